@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native IDEAL-NeRF render_rays path.
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W     # the reference algorithm on the host CPU cores
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): one step = one full 450x450 HeadNeRF frame, 202 500 rays,
+64 coarse + 128 importance samples (256 FaceNeRF evaluations per ray), random-init FaceNeRF
+(dim_aud=64, dim_expr=76, latent 32) with the normalised-density preset, synthetic camera/background/
+audio/expression codes (oracle.render_oracle.synthetic_frame).  At N GPUs every step renders a group
+of N frames whose rays are block-partitioned across the ranks (each rank renders 1/N of every frame of
+the group = 202 500 rays per rank per step: weak scaling) and the rendered bands are gathered on rank 0
+over NCCL.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = W = 450
+N_RAYS = H * W
+S1, S_IMP = 64, 128
+FLOP_PER_POINT_FWD = 1_121_280           # 560 640 MAC, conditioning folded, K unpadded
+METRIC = "rays/sec render (64+128 samples), 450x450 frame"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace('.', '', 1).isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [float(r[1]) for r in self.rows if r[1].replace('.', '', 1).isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the reference algorithm on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rays_per_s(n_rays, steps, warmup):
+    from oracle import render_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    fr = O.synthetic_frame(0)
+    c, f = O.init_face_nerf(1), O.init_face_nerf(2)
+    sub = torch.arange(0, N_RAYS, N_RAYS // n_rays)[:n_rays]
+    rays, bc = fr["rays"][sub].contiguous(), fr["bc_rgb"][sub].contiguous()
+    c = O.normalise_density(c, rays, fr["aud"], fr["expr"], fr["latent"])
+    f = O.normalise_density(f, rays, fr["aud"], fr["expr"], fr["latent"])
+    ts = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.render_rays(rays, bc, c, f, fr["aud"], fr["expr"], fr["latent"])
+            if i >= warmup:
+                ts.append(time.perf_counter() - t0)
+    dt = sum(ts) / len(ts)
+    return n_rays / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = 2048
+    v, dt, cores = cpu_reference_rays_per_s(n, args.steps, max(1, args.warmup))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "HeadNeRF 450x450 frame render (coarse 64 + fine 192 samples), reference algorithm on host CPU",
+                       "sample": f"{n} rays of the frame per step"},
+            "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
+                             "sample": f"{n} of 202500 frame rays per step, torch {torch.__version__} fp32, "
+                                       f"{torch.backends.cpu.get_cpu_capability()}"},
+            "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------
+def build_network(mode, dev):
+    import ideal_nerf_b200 as M
+    from ideal_nerf_b200 import synthetic as S, ops
+    cam, fr = S.camera(), S.frame_inputs(0)
+    a = M.default_args(dim_aud=64, dim_expr=76, perturb=1.0, mlp_mode=mode, N_samples=S1, N_importance=S_IMP,
+                       near=S.NEAR, far=S.FAR)
+    net = M.Network(H, W, cam["focal"], S.NEAR, S.FAR, 1 << 20, None, S1, S_IMP, args=a)
+    torch.manual_seed(1234)
+    net.apply(M.init_weights)                       # xavier-uniform, bias 0.01 (audio_exp_nerf.py:442-448)
+    net = net.to(dev).eval()
+    rays = ops.get_rays_packed(H, W, cam["focal"], cam["c2w"].to(dev), S.NEAR, S.FAR)[::197].contiguous()
+    for fn in (net.face_nerf_coarse, net.face_nerf_fine):
+        S.normalise_density_(fn, rays, fr["aud"].to(dev), fr["expr"].to(dev), fr["latent"].to(dev))
+    return M, net, fr, cam
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    M, net, fr, cam = build_network(args.mode, dev)
+    from ideal_nerf_b200 import ops
+    from ideal_nerf_b200.frame import FrameRenderer, band
+    M._lib.check(M.lib().inerf_device_check(), "inerf_device_check")
+    fr_r = FrameRenderer(net, rank, world)
+
+    # ---- inputs: pinned host copies (e2e) and resident device copies (value) ----------------------
+    host = {"pose": fr["pose"].pin_memory(), "aud": fr["aud"].pin_memory(), "expr": fr["expr"].pin_memory(),
+            "latent": fr["latent"].pin_memory(), "bc": fr["bc_rgb"].pin_memory()}
+    res = {k: v.to(dev) for k, v in host.items()}
+    frames = world                                   # frames per step (weak scaling: 202 500 rays per rank per step)
+    lo, hi = band(N_RAYS, rank, world)
+
+    def step_resident():
+        out = None
+        for _ in range(frames):
+            ret, _ = fr_r.render_band(res["pose"], res["aud"], res["expr"], res["latent"], res["bc"], perturb=1.0)
+            out = fr_r.gather_image(ret["rgb_map"], N_RAYS)
+        return out
+
+    out_h = torch.empty((N_RAYS, 3)).pin_memory()
+    h2d = sum(host[k].numel() * 4 for k in host)
+
+    def step_e2e():
+        """Public API with HOST buffers: H2D of the frame's inputs, render, gather, D2H of the image."""
+        for _ in range(frames):
+            d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            if world == 1:
+                rgb = net.render_dynamic_face(H, W, net.focal, d["expr"], d["pose"], d["latent"], render_poses=d["pose"][:3, :4],
+                                              chunk=1 << 20, near=net.near, far=net.far, bc_rgb=d["bc"].reshape(H, W, 3),
+                                              aud_para=d["aud"], perturb=1.0)[0].reshape(-1, 3)
+            else:
+                rgb = fr_r.render_frame(d["pose"], d["aud"], d["expr"], d["latent"], d["bc"], perturb=1.0)
+            if rank == 0:
+                out_h.copy_(rgb, non_blocking=True)
+        torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ops.LAUNCHES["count"] = 0
+    with ops.kernel_timing() as kt:
+        total_ms = timed(step_resident, args.steps)
+    launches = ops.LAUNCHES["count"]
+    clocks = sampler.stop() if sampler else None
+    ksum = kt.summary()
+
+    for _ in range(2):
+        step_e2e()
+    t_e2e = timed(step_e2e, args.steps)
+
+    rays_per_step = N_RAYS * frames                   # all ranks together
+    value = rays_per_step * args.steps / (total_ms * 1e-3)
+    e2e_value = rays_per_step * args.steps / (t_e2e * 1e-3)
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        n_mlp, mlp_ms = ksum.get("inerf_mlp_fwd", (0, 0.0))
+        # dominant kernel: FaceNeRF forward.  Algorithmic FLOPs of the launches in the timed region / their event time.
+        pts_per_step_rank = (hi - lo) * (S1 + S1 + S_IMP) * frames
+        mlp_flops = pts_per_step_rank * args.steps * FLOP_PER_POINT_FWD
+        achieved = mlp_flops / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else None
+        peak = pk["bf16_tflops_sustained"]
+        n_cmp, cmp_ms = ksum.get("inerf_composite_fwd", (0, 0.0))
+        cmp_bytes = (hi - lo) * frames * args.steps * ((24 * S1 + 48) + (24 * (S1 + S_IMP) + 48))
+        line = {
+            "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.mode == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": "HeadNeRF full 450x450 frame render (coarse 64 + fine 192 samples), FaceNeRF dim_aud=64 dim_expr=76",
+                       "frames_per_step": frames, "rays_per_rank_per_step": (hi - lo) * frames, "mlp_mode": args.mode,
+                       "perturb": 1.0, "l2": "inputs larger than L2 (raw 207+622 MB per frame pass)",
+                       "parallelism": f"rays block-partitioned over {world} GPU(s), NCCL gather of bands"},
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d * frames,
+                    "d2h_bytes_per_step": N_RAYS * 3 * 4 * frames, "ms_per_step": t_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "inerf_mlp_fwd", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "peak_kind": f"bf16 dense sustained, {pk_kind}", "launches": n_mlp, "kernel_ms_total": mlp_ms,
+                         "share_of_step": mlp_ms / total_ms if total_ms else None},
+            "roofline_composite": {"bound": "hbm", "kernel": "inerf_composite_fwd",
+                                   "achieved": cmp_bytes / (cmp_ms * 1e-3) / 1e9 if cmp_ms > 0 else None,
+                                   "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                   "frac": (cmp_bytes / (cmp_ms * 1e-3) / 1e9 / pk["hbm_gbs"]) if cmp_ms > 0 else None,
+                                   "launches": n_cmp, "kernel_ms_total": cmp_ms},
+            "kernels_ms": {k: round(v[1], 3) for k, v in ksum.items()},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, dt, cores = cpu_reference_rays_per_s(3072, 2, 1)
+            line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
+                                    "sample": f"3072 of 202500 frame rays, 1 warm-up + 2 timed runs ({dt:.2f} s each), "
+                                              f"torch {torch.__version__} fp32 {torch.backends.cpu.get_cpu_capability()}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", type=str, default=os.environ.get("INERF_BENCH_MODE", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

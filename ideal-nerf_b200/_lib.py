@@ -1,0 +1,109 @@
+"""ctypes binding of libinerf_b200.so (the C ABI declared in include/inerf_b200.h) and its builder.
+
+The library is the product: there is no Python / PyTorch / CPU fallback.  ``lib()`` raises if the
+shared object has not been built, and every entry point raises when the current device is not
+sm_100 -- nothing here routes to ``oracle/``.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+REPO_ROOT = os.path.dirname(PKG_DIR)
+CSRC = os.path.join(PKG_DIR, "csrc")
+SO_PATH = os.path.join(PKG_DIR, "libinerf_b200.so")
+SOURCES = ["api.cu", "rays.cu", "composite.cu", "sample_pdf.cu", "mlp_fp32.cu", "mlp_bf16.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--shared"]
+
+INERF_MLP_FP32, INERF_MLP_BF16 = 0, 1
+INERF_PDF_EXACT_TORCH_CPU, INERF_PDF_FAST = 0, 1
+N_PARAMS = 26
+
+c_f32p = ctypes.c_void_p     # device pointers travel as opaque addresses
+c_stream = ctypes.c_void_p
+
+
+class InerfNetDims(ctypes.Structure):
+    _fields_ = [("dim_aud", ctypes.c_int32), ("dim_expr", ctypes.c_int32), ("dim_latent", ctypes.c_int32),
+                ("width", ctypes.c_int32), ("depth", ctypes.c_int32), ("in_xyz", ctypes.c_int32),
+                ("in_views", ctypes.c_int32)]
+
+
+ParamArray = ctypes.c_void_p * N_PARAMS
+
+_I, _F, _P, _L, _SZP = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_size_t)
+_DIMS = ctypes.POINTER(InerfNetDims)
+_PARAMS = ctypes.POINTER(ctypes.c_void_p)
+
+# name -> (restype, argtypes); must list every symbol include/inerf_b200.h declares
+SIGNATURES = {
+    "inerf_version": (_I, []),
+    "inerf_last_error": (ctypes.c_char_p, []),
+    "inerf_device_check": (_I, []),
+    "inerf_get_rays": (_I, [_I, _I, _F, _F, _F, _P, _I, _F, _F, _P, _P]),
+    "inerf_pack_rays": (_I, [_P, _P, _I, _F, _F, _P, _P]),
+    "inerf_posenc": (_I, [_P, _L, _I, _I, _P, _P]),
+    "inerf_sample_coarse": (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P]),
+    "inerf_composite_fwd": (_I, [_P, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "inerf_composite_bwd": (_I, [_P, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "inerf_head_torso_blend": (_I, [_P, _P, _P, _I, _P, _P]),
+    "inerf_sample_pdf": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P, _I, _P, _P, _P]),
+    "inerf_importance_sample": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P]),
+    "inerf_mlp_cond_floats": (_I, [_DIMS, _SZP]),
+    "inerf_mlp_fold_cond": (_I, [_DIMS, _PARAMS, _P, _P, _P, _P, _P]),
+    "inerf_mlp_packed_bytes": (_I, [_I, _DIMS, _SZP]),
+    "inerf_mlp_pack": (_I, [_I, _DIMS, _PARAMS, _P, _P]),
+    "inerf_mlp_fwd": (_I, [_I, _DIMS, _PARAMS, _P, _P, _P, _I, _P, _I, _I, _P, _P]),
+    "inerf_mlp_fwd_embedded": (_I, [_I, _DIMS, _PARAMS, _P, _P, _P, _L, _P, _P]),
+}
+
+_lib = None
+
+
+def _stale():
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(REPO_ROOT, "include", "inerf_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu for sm_100a into ideal-nerf_b200/libinerf_b200.so (nvcc cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return SO_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libinerf_b200.so")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH + ".tmp"] + SOURCES
+    r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    os.replace(SO_PATH + ".tmp", SO_PATH)
+    if verbose:
+        print(r.stderr)
+    return SO_PATH
+
+
+def lib():
+    """The loaded C-ABI library.  Fails loudly when it is missing -- there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(nvcc, sm_100a).  ideal-nerf_b200 has no CPU or PyTorch fallback.")
+        L = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)           # AttributeError here = header/library mismatch
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().inerf_last_error().decode("utf-8", "replace")
+        kind = "CUDA error" if rc > 0 else "argument error"
+        raise RuntimeError(f"{what}: {kind} {rc}: {msg}")

@@ -1,0 +1,441 @@
+// FaceNeRF MLP, fp32 mode: exact-arithmetic path (FFMA, fp32 everywhere) + conditioning fold +
+// the C-ABI dispatch for both MLP modes.
+//
+// Reference: models/face_nerf.py:40-80 (forward), NeRFs/HeadNeRF/train/audio_exp_nerf.py:332,376-394
+// (points, embedding, netchunk loop), NeRFs/HeadNeRF/helper.py:174-204 (positional encoding).
+//
+// The fp32 mode is the "max-abs <= 1e-3 vs the reference" mode of BASELINE.json and the on-device
+// yardstick for the bf16 tensor-core kernel (mlp_bf16.cu).  One CTA owns a tile of 64 points and
+// keeps every activation in shared memory from the positional encoding to the (r,g,b,sigma) output;
+// only the weights stream in (from L2, nn.Linear layout, no repack so training can update them in
+// place).  Each layer is a 64 x N x K register-tiled SGEMM: 256 threads, 8 points x 8 (or 4)
+// features per thread, K consumed in 16-wide slices double-buffered through shared memory.
+//
+// Conditioning (aud | expr/3 | latent) is constant over the call, so its weight columns are folded
+// into the biases once per call by inerf_mlp_fold_cond and the per-point
+// network is 63->256, 4x(256->256), 319->256, 2x(256->256), {256->1, 283->128, 2x(128->128), 128->3}.
+#include "mlp_common.cuh"
+
+using namespace inerf;
+
+namespace {
+
+constexpr int TM = 64;            // points per tile
+constexpr int KC = 16;            // K slice
+constexpr int NTHREADS = 256;
+
+// activation element (k, m) of a [K][64] k-major buffer; 16-byte chunks are XOR-swizzled by k/4 so
+// that the epilogue's column-of-rows float4 stores are bank-conflict free.
+__device__ __forceinline__ int act_idx(int k, int m) { return k * TM + ((((m >> 2) ^ (k >> 2)) & 15) << 2) + (m & 3); }
+
+struct Seg {
+    const float* src;   // smem activations [K][64]
+    int k;              // rows used
+    int wcol;           // first weight column
+};
+
+template <int N>
+__device__ __forceinline__ void load_w_regs(float (&r)[N / 16], const float* __restrict__ W, int ldw, const Seg& sg,
+                                            int k0, int tid) {
+    constexpr int PER = N / 16;
+    const int n = tid % N, kk0 = (tid / N) * PER;
+    const float* row = W + (size_t)n * ldw + sg.wcol + k0 + kk0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) r[i] = (k0 + kk0 + i < sg.k) ? __ldg(row + i) : 0.0f;
+}
+
+template <int N>
+__device__ __forceinline__ void store_w_smem(const float (&r)[N / 16], float* ws, int tid) {
+    constexpr int PER = N / 16;
+    const int n = tid % N, kk0 = (tid / N) * PER;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) ws[(kk0 + i) * N + n] = r[i];
+}
+
+// out[n][m] = act( sum_k W[n][wcol+k] * in[k][m] + bias[n] )   for one 64-point tile.
+// N = 256: thread owns features {4tn..4tn+3} U {128+4tn..}, N = 128: {4tn..4tn+3}; points 8tm..8tm+7.
+template <int N>
+__device__ void gemm_layer(const float* __restrict__ W, int ldw, const Seg* segs, int nseg,
+                           const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ wsm) {
+    constexpr int NT = N / 32;
+    const int tid = threadIdx.x, tn = tid & 31, tm = tid >> 5;
+    float acc[NT][8];
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
+
+    int nchunks = 0;
+    for (int sidx = 0; sidx < nseg; ++sidx) nchunks += (segs[sidx].k + KC - 1) / KC;
+
+    float wr[N / 16];
+    int seg_i = 0, k0 = 0;
+    load_w_regs<N>(wr, W, ldw, segs[0], 0, tid);
+    store_w_smem<N>(wr, wsm, tid);
+    __syncthreads();
+    for (int c = 0; c < nchunks; ++c) {
+        // position of the next chunk
+        int nseg_i = seg_i, nk0 = k0 + KC;
+        if (nk0 >= segs[seg_i].k) { nseg_i = seg_i + 1; nk0 = 0; }
+        const bool more = c + 1 < nchunks;
+        if (more) load_w_regs<N>(wr, W, ldw, segs[nseg_i], nk0, tid);
+
+        const float* ws = wsm + (c & 1) * (KC * N);
+        const float* in = segs[seg_i].src;
+        const int kmax = min(KC, segs[seg_i].k - k0);
+#pragma unroll 4
+        for (int kk = 0; kk < KC; ++kk) {
+            if (kk < kmax) {
+                const int k = k0 + kk;
+                const int sw = (k >> 2) & 15;
+                const float4 a0 = *reinterpret_cast<const float4*>(in + k * TM + (((2 * tm) ^ sw) << 2));
+                const float4 a1 = *reinterpret_cast<const float4*>(in + k * TM + (((2 * tm + 1) ^ sw) << 2));
+                const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                float b[NT];
+                const float4 b0 = *reinterpret_cast<const float4*>(ws + kk * N + 4 * tn);
+                b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+                if constexpr (NT == 8) {
+                    const float4 b1 = *reinterpret_cast<const float4*>(ws + kk * N + 128 + 4 * tn);
+                    b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+                }
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(b[j], a[i], acc[j][i]);
+            }
+        }
+        if (more) store_w_smem<N>(wr, wsm + ((c + 1) & 1) * (KC * N), tid);
+        seg_i = nseg_i; k0 = nk0;
+        __syncthreads();
+    }
+    // epilogue: bias + ReLU, write the next layer's k-major activations
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        const int n = 4 * tn + (j & 3) + 128 * (j >> 2);
+        const float b = __ldg(bias + n);
+        const int sw = (n >> 2) & 15;
+        float4 o0, o1;
+        o0.x = fmaxf(acc[j][0] + b, 0.f); o0.y = fmaxf(acc[j][1] + b, 0.f);
+        o0.z = fmaxf(acc[j][2] + b, 0.f); o0.w = fmaxf(acc[j][3] + b, 0.f);
+        o1.x = fmaxf(acc[j][4] + b, 0.f); o1.y = fmaxf(acc[j][5] + b, 0.f);
+        o1.z = fmaxf(acc[j][6] + b, 0.f); o1.w = fmaxf(acc[j][7] + b, 0.f);
+        *reinterpret_cast<float4*>(out + n * TM + (((2 * tm) ^ sw) << 2)) = o0;
+        *reinterpret_cast<float4*>(out + n * TM + (((2 * tm + 1) ^ sw) << 2)) = o1;
+    }
+    __syncthreads();
+}
+
+// dot products of NOUT tiny output rows with a [K][64] activation buffer; result in red[o][m]
+template <int NOUT>
+__device__ void small_head(const float* __restrict__ W, int K, const float* __restrict__ in, float* __restrict__ red) {
+    const int tid = threadIdx.x, m = tid & 63, part = tid >> 6;
+    const int kq = K / 4;
+    float acc[NOUT];
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) acc[o] = 0.f;
+    for (int k = part * kq; k < (part + 1) * kq; ++k) {
+        const float a = in[act_idx(k, m)];
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) acc[o] = fmaf(__ldg(W + o * K + k), a, acc[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) red[(o * 4 + part) * TM + m] = acc[o];
+    __syncthreads();
+}
+
+template <bool EMBEDDED>
+__global__ void __launch_bounds__(NTHREADS, 1) mlp_fp32_kernel(MlpArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    float* H0 = sm;                      // [256][64]
+    float* H1 = H0 + 256 * TM;           // [256][64]
+    float* PE = H1 + 256 * TM;           // [64][64]   gamma_10(p), 63 rows used
+    float* DIR = PE + 64 * TM;           // [32][64]   gamma_4(viewdir), 27 rows used
+    float* WS = DIR + 32 * TM;           // 2 x [16][256]
+    float* RED = WS + 2 * KC * 256;      // [16][64] head partials
+    float* OUTB = RED + 16 * TM;         // [64][4]
+
+    const int tid = threadIdx.x;
+    const CondLayout cl{256, 128};
+    const long long ntiles = (a.P + TM - 1) / TM;
+    const int C = a.cond_dim;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // ---- inputs: positional encodings of the tile's points --------------------------------
+        {
+            const int m = tid & 63, part = tid >> 6;
+            long long p = tile * TM + m;
+            const bool ok = p < a.P;
+            if (!ok) p = a.P - 1;
+            if constexpr (EMBEDDED) {
+                const float* xr = a.x + p * 90;
+                for (int k = part; k < 64; k += 4) PE[act_idx(k, m)] = (k < 63) ? xr[k] : 0.f;
+                for (int k = part; k < 32; k += 4) DIR[act_idx(k, m)] = (k < 27) ? xr[63 + k] : 0.f;
+            } else {
+                const long long ray = p / a.s;
+                const float* r = a.rays + ray * a.ray_stride;
+                const float zz = a.z[p];
+                float pos[3], vd[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    pos[c] = __fadd_rn(r[c], __fmul_rn(r[3 + c], zz));     // o + d*z   (:332)
+                    vd[c] = r[a.ray_stride - 3 + c];                       // rays[:, -3:]
+                }
+                if (part == 0) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { PE[act_idx(c, m)] = pos[c]; DIR[act_idx(c, m)] = vd[c]; }
+                    PE[act_idx(63, m)] = 0.f;
+                }
+                if (part == 1)
+                    for (int k = 27; k < 32; ++k) DIR[act_idx(k, m)] = 0.f;
+                for (int f = part; f < 10; f += 4) {
+                    const float sc = (float)(1 << f);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        float sn, cs;
+                        sincosf(pos[c] * sc, &sn, &cs);
+                        PE[act_idx(3 + 6 * f + c, m)] = sn;
+                        PE[act_idx(6 + 6 * f + c, m)] = cs;
+                    }
+                }
+                {
+                    const int f = part;                                    // 4 view frequencies, 4 parts
+                    const float sc = (float)(1 << f);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        float sn, cs;
+                        sincosf(vd[c] * sc, &sn, &cs);
+                        DIR[act_idx(3 + 6 * f + c, m)] = sn;
+                        DIR[act_idx(6 + 6 * f + c, m)] = cs;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- trunk -----------------------------------------------------------------------------
+        Seg sg[2];
+        sg[0] = {PE, 63, 0};
+        gemm_layer<256>(a.w[0], 63 + C, sg, 1, a.cond + cl.pts(0), H0, WS);
+        float* cur = H0;
+        float* nxt = H1;
+        for (int l = 1; l < 8; ++l) {
+            if (l == 5) {
+                sg[0] = {PE, 63, 0};
+                sg[1] = {cur, 256, 63 + C};
+                gemm_layer<256>(a.w[2 * l], 319 + C, sg, 2, a.cond + cl.pts(l), nxt, WS);
+            } else {
+                sg[0] = {cur, 256, 0};
+                gemm_layer<256>(a.w[2 * l], 256, sg, 1, a.cond + cl.pts(l), nxt, WS);
+            }
+            float* t = cur; cur = nxt; nxt = t;
+        }
+        // cur = relu(pts_linears.7(...));  sigma = alpha_linear(cur)
+        small_head<1>(a.w[P_ALPHA_W], 256, cur, RED);
+        if (tid < TM) {
+            float s = (RED[0 * TM + tid] + RED[1 * TM + tid]) + (RED[2 * TM + tid] + RED[3 * TM + tid]);
+            OUTB[tid * 4 + 3] = s + a.cond[cl.alpha_b()];
+        }
+        // ---- view branch -----------------------------------------------------------------------
+        sg[0] = {cur, 256, 0};
+        sg[1] = {DIR, 27, 256};
+        gemm_layer<128>(a.w[P_VIEWS_W], 283 + a.dim_expr, sg, 2, a.cond + cl.views(0), nxt, WS);
+        sg[0] = {nxt, 128, 0};
+        gemm_layer<128>(a.w[P_VIEWS_W + 2], 128, sg, 1, a.cond + cl.views(1), cur, WS);
+        sg[0] = {cur, 128, 0};
+        gemm_layer<128>(a.w[P_VIEWS_W + 4], 128, sg, 1, a.cond + cl.views(2), nxt, WS);
+        small_head<3>(a.w[P_RGB_W], 128, nxt, RED);
+        if (tid < 3 * TM) {
+            const int o = tid / TM, m = tid - o * TM;
+            float s = (RED[(o * 4 + 0) * TM + m] + RED[(o * 4 + 1) * TM + m]) +
+                      (RED[(o * 4 + 2) * TM + m] + RED[(o * 4 + 3) * TM + m]);
+            OUTB[m * 4 + o] = s + a.cond[cl.rgb_b() + o];
+        }
+        __syncthreads();
+        if (tid < TM) {
+            const long long p = tile * TM + tid;
+            if (p < a.P) reinterpret_cast<float4*>(a.out)[p] = *reinterpret_cast<const float4*>(OUTB + tid * 4);
+        }
+        __syncthreads();
+    }
+}
+
+constexpr size_t FP32_SMEM = (size_t)(2 * 256 * TM + 64 * TM + 32 * TM + 2 * KC * 256 + 16 * TM + TM * 4) * sizeof(float);
+
+// ---------------------------------------------------------------------------------------------
+// conditioning fold
+// ---------------------------------------------------------------------------------------------
+struct FoldArgs {
+    const float* w[INERF_N_PARAMS];
+    const float* aud; const float* expr; const float* latent;
+    int da, de, dl;
+    float* cond;
+};
+
+__global__ void fold_cond_kernel(FoldArgs f) {
+    __shared__ float c[1024];
+    const int C = f.da + f.de + f.dl;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        float v;
+        if (i < f.da) v = f.aud[i];
+        else if (i < f.da + f.de) v = __fdiv_rn(__fmul_rn(f.expr[i - f.da], 1.0f), 3.0f);   // expr * 1 / 3  (face_nerf.py:49)
+        else v = f.latent[i - f.da - f.de];
+        c[i] = v;
+    }
+    __syncthreads();
+    const CondLayout cl{256, 128};
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    if (b < 8) {                                  // pts_linears.b
+        const float* W = f.w[2 * b];
+        const float* B = f.w[2 * b + 1];
+        const int ldw = (b == 0) ? 63 + C : (b == 5 ? 319 + C : 256);
+        const bool folded = (b == 0 || b == 5) && C > 0;
+        for (int n = warp; n < 256; n += nwarp) {
+            float s = 0.f;
+            if (folded)
+                for (int j = lane; j < C; j += 32) s = fmaf(W[(size_t)n * ldw + 63 + j], c[j], s);
+            s = warp_sum(s);
+            if (lane == 0) f.cond[cl.pts(b) + n] = B[n] + s;
+        }
+    } else if (b < 11) {                          // views_linears.(b-8)
+        const int v = b - 8;
+        const float* W = f.w[P_VIEWS_W + 2 * v];
+        const float* B = f.w[P_VIEWS_W + 2 * v + 1];
+        const int ldw = 283 + f.de;
+        for (int n = warp; n < 128; n += nwarp) {
+            float s = 0.f;
+            if (v == 0)
+                for (int j = lane; j < f.de; j += 32) s = fmaf(W[(size_t)n * ldw + 283 + j], c[f.da + j], s);
+            s = warp_sum(s);
+            if (lane == 0) f.cond[cl.views(v) + n] = B[n] + s;
+        }
+    } else if (threadIdx.x < 4) {
+        f.cond[cl.alpha_b() + threadIdx.x] = threadIdx.x == 0 ? f.w[P_ALPHA_B][0] : f.w[P_RGB_B][threadIdx.x - 1];
+    }
+}
+
+int fill_args(MlpArgs& a, const InerfNetDims* dims, const float* const* params_host, const float* cond) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (!params_host || !cond) return fail(INERF_E_ARG, "mlp: NULL params/cond");
+    for (int i = 0; i < INERF_N_PARAMS; ++i) {
+        if (!params_host[i]) return fail(INERF_E_ARG, "mlp: NULL parameter pointer");
+        a.w[i] = params_host[i];
+    }
+    a.cond = cond;
+    a.cond_dim = dims->dim_aud + dims->dim_expr + dims->dim_latent;
+    a.dim_expr = dims->dim_expr;
+    return INERF_OK;
+}
+
+}  // namespace
+
+namespace inerf {
+
+int mlp_fp32_launch(const MlpArgs& a, bool embedded, cudaStream_t st) {
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_dev != dev) {
+        cudaError_t e1 = cudaFuncSetAttribute(mlp_fp32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FP32_SMEM);
+        cudaError_t e2 = cudaFuncSetAttribute(mlp_fp32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FP32_SMEM);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {
+            set_error("mlp_fp32: cudaFuncSetAttribute(%zu B smem): %s", FP32_SMEM, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+            return (int)(e1 != cudaSuccess ? e1 : e2);
+        }
+        configured_dev = dev;
+    }
+    long long ntiles = (a.P + TM - 1) / TM;
+    int grid = (int)(ntiles < (long long)num_sms() ? ntiles : (long long)num_sms());
+    if (embedded) mlp_fp32_kernel<true><<<grid, NTHREADS, FP32_SMEM, st>>>(a);
+    else mlp_fp32_kernel<false><<<grid, NTHREADS, FP32_SMEM, st>>>(a);
+    return check_launch("inerf_mlp_fwd[fp32]");
+}
+
+}  // namespace inerf
+
+extern "C" int inerf_mlp_cond_floats(const InerfNetDims* dims, size_t* n_floats) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (!n_floats) return fail(INERF_E_ARG, "inerf_mlp_cond_floats: NULL");
+    *n_floats = (size_t)CondLayout{256, 128}.total();
+    return INERF_OK;
+}
+
+extern "C" int inerf_mlp_fold_cond(const InerfNetDims* dims, const float* const* params_host, const float* aud,
+                                   const float* expr, const float* latent, float* cond, void* stream) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (!params_host || !cond) return fail(INERF_E_ARG, "inerf_mlp_fold_cond: NULL pointer");
+    if ((dims->dim_aud > 0 && !aud) || (dims->dim_expr > 0 && !expr) || (dims->dim_latent > 0 && !latent))
+        return fail(INERF_E_ARG, "inerf_mlp_fold_cond: conditioning vector missing for a non-zero dim");
+    FoldArgs f{};
+    for (int i = 0; i < INERF_N_PARAMS; ++i) {
+        if (!params_host[i]) return fail(INERF_E_ARG, "inerf_mlp_fold_cond: NULL parameter pointer");
+        f.w[i] = params_host[i];
+    }
+    f.aud = aud; f.expr = expr; f.latent = latent;
+    f.da = dims->dim_aud; f.de = dims->dim_expr; f.dl = dims->dim_latent;
+    f.cond = cond;
+    fold_cond_kernel<<<12, 256, 0, as_stream(stream)>>>(f);
+    return check_launch("inerf_mlp_fold_cond");
+}
+
+extern "C" int inerf_mlp_packed_bytes(int mode, const InerfNetDims* dims, size_t* bytes) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (!bytes) return fail(INERF_E_ARG, "inerf_mlp_packed_bytes: NULL");
+    if (mode == INERF_MLP_FP32) { *bytes = 0; return INERF_OK; }
+    if (mode == INERF_MLP_BF16) return mlp_bf16_packed_bytes(dims, bytes);
+    return fail(INERF_E_UNSUPPORTED, "inerf_mlp_packed_bytes: unknown mode");
+}
+
+extern "C" int inerf_mlp_pack(int mode, const InerfNetDims* dims, const float* const* params_host, void* packed,
+                              void* stream) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (mode == INERF_MLP_FP32) return INERF_OK;
+    if (mode == INERF_MLP_BF16) {
+        if (!params_host || !packed) return fail(INERF_E_ARG, "inerf_mlp_pack: NULL pointer");
+        return mlp_bf16_pack(dims, params_host, packed, as_stream(stream));
+    }
+    return fail(INERF_E_UNSUPPORTED, "inerf_mlp_pack: unknown mode");
+}
+
+extern "C" int inerf_mlp_fwd(int mode, const InerfNetDims* dims, const float* const* params_host, const void* packed,
+                             const float* cond, const float* rays, int ray_stride, const float* z, int n, int s,
+                             float* raw, void* stream) {
+    MlpArgs a{};
+    int rc = fill_args(a, dims, params_host, cond);
+    if (rc) return rc;
+    if (n < 0 || s <= 0 || ray_stride < 11) return fail(INERF_E_SHAPE, "inerf_mlp_fwd: bad n/s/ray_stride (rays need the viewdir columns)");
+    if (n == 0) return INERF_OK;
+    if (!rays || !z || !raw) return fail(INERF_E_ARG, "inerf_mlp_fwd: NULL pointer");
+    if ((uintptr_t)raw & 15) return fail(INERF_E_ALIGN, "inerf_mlp_fwd: raw must be 16-byte aligned");
+    a.rays = rays; a.ray_stride = ray_stride; a.z = z; a.s = s;
+    a.P = (long long)n * s; a.out = raw; a.packed = packed;
+    if (mode == INERF_MLP_FP32) return mlp_fp32_launch(a, false, as_stream(stream));
+    if (mode == INERF_MLP_BF16) {
+        if (!packed) return fail(INERF_E_ARG, "inerf_mlp_fwd: bf16 mode needs packed weights");
+        return mlp_bf16_launch(a, false, as_stream(stream));
+    }
+    return fail(INERF_E_UNSUPPORTED, "inerf_mlp_fwd: unknown mode");
+}
+
+extern "C" int inerf_mlp_fwd_embedded(int mode, const InerfNetDims* dims, const float* const* params_host,
+                                      const void* packed, const float* cond, const float* x, int64_t p, float* out,
+                                      void* stream) {
+    MlpArgs a{};
+    int rc = fill_args(a, dims, params_host, cond);
+    if (rc) return rc;
+    if (p < 0) return fail(INERF_E_SHAPE, "inerf_mlp_fwd_embedded: p < 0");
+    if (p == 0) return INERF_OK;
+    if (!x || !out) return fail(INERF_E_ARG, "inerf_mlp_fwd_embedded: NULL pointer");
+    if ((uintptr_t)out & 15) return fail(INERF_E_ALIGN, "inerf_mlp_fwd_embedded: out must be 16-byte aligned");
+    a.x = x; a.P = p; a.out = out; a.packed = packed; a.s = 1;
+    if (mode == INERF_MLP_FP32) return mlp_fp32_launch(a, true, as_stream(stream));
+    if (mode == INERF_MLP_BF16) {
+        if (!packed) return fail(INERF_E_ARG, "inerf_mlp_fwd_embedded: bf16 mode needs packed weights");
+        return mlp_bf16_launch(a, true, as_stream(stream));
+    }
+    return fail(INERF_E_UNSUPPORTED, "inerf_mlp_fwd_embedded: unknown mode");
+}

@@ -1,0 +1,165 @@
+// Ray generation / packing, positional encoding, stratified coarse depths, head/torso blend.
+//
+// All arithmetic that feeds the bit-exact sample_pdf gate uses explicit round-to-nearest
+// intrinsics (__fmul_rn/__fadd_rn are never contracted into FMA), so the depths equal the
+// reference's tensor-op-at-a-time fp32 values.
+#include "common.cuh"
+
+using namespace inerf;
+
+// ---------------------------------------------------------------------------------------------
+// get_rays + packing.  helper.py:228-243, audio_exp_nerf.py:409-427
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_ray(float* __restrict__ r, float ox, float oy, float oz, float dx, float dy,
+                                          float dz, float near_, float far_) {
+    // viewdirs = d / ||d||_2   (torch.norm = sqrt(sum of squares), then a true division)
+    float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    r[0] = ox; r[1] = oy; r[2] = oz;
+    r[3] = dx; r[4] = dy; r[5] = dz;
+    r[6] = near_; r[7] = far_;
+    r[8] = __fdiv_rn(dx, nrm); r[9] = __fdiv_rn(dy, nrm); r[10] = __fdiv_rn(dz, nrm);
+}
+
+__global__ void get_rays_kernel(int H, int W, float focal, float cx, float cy, const float* __restrict__ c2w,
+                                int rs, float near_, float far_, float* __restrict__ rays) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= H * W) return;
+    int row = idx / W, col = idx - row * W;
+    // camera-frame direction ((i-cx)/f, -(j-cy)/f, -1)
+    float c0 = __fdiv_rn(__fsub_rn((float)col, cx), focal);
+    float c1 = -__fdiv_rn(__fsub_rn((float)row, cy), focal);
+    float c2 = -1.0f;
+    float d[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        // torch.sum(dirs[..., None, :] * c2w[:3,:3], -1): products rounded, added left to right
+        float a = __fmul_rn(c0, c2w[r * rs + 0]);
+        float b = __fmul_rn(c1, c2w[r * rs + 1]);
+        float c = __fmul_rn(c2, c2w[r * rs + 2]);
+        d[r] = __fadd_rn(__fadd_rn(a, b), c);
+    }
+    store_ray(rays + (size_t)idx * 11, c2w[3], c2w[rs + 3], c2w[2 * rs + 3], d[0], d[1], d[2], near_, far_);
+}
+
+__global__ void pack_rays_kernel(const float* __restrict__ o, const float* __restrict__ d, int n, float near_,
+                                 float far_, float* __restrict__ rays) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    store_ray(rays + (size_t)idx * 11, o[idx * 3], o[idx * 3 + 1], o[idx * 3 + 2], d[idx * 3], d[idx * 3 + 1],
+              d[idx * 3 + 2], near_, far_);
+}
+
+extern "C" int inerf_get_rays(int H, int W, float focal, float cx, float cy, const float* c2w, int c2w_row_stride,
+                              float near_, float far_, float* rays, void* stream) {
+    if (!c2w || !rays) return fail(INERF_E_ARG, "inerf_get_rays: NULL pointer");
+    if (H <= 0 || W <= 0 || (int64_t)H * W > (1 << 30) || c2w_row_stride < 4)
+        return fail(INERF_E_SHAPE, "inerf_get_rays: bad H/W/c2w_row_stride");
+    int n = H * W;
+    get_rays_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(H, W, focal, cx, cy, c2w, c2w_row_stride, near_,
+                                                                    far_, rays);
+    return check_launch("inerf_get_rays");
+}
+
+extern "C" int inerf_pack_rays(const float* rays_o, const float* rays_d, int n, float near_, float far_, float* rays,
+                               void* stream) {
+    if (n < 0) return fail(INERF_E_SHAPE, "inerf_pack_rays: n < 0");
+    if (n == 0) return INERF_OK;
+    if (!rays_o || !rays_d || !rays) return fail(INERF_E_ARG, "inerf_pack_rays: NULL pointer");
+    pack_rays_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(rays_o, rays_d, n, near_, far_, rays);
+    return check_launch("inerf_pack_rays");
+}
+
+// ---------------------------------------------------------------------------------------------
+// positional encoding.  helper.py:174-224
+// ---------------------------------------------------------------------------------------------
+__global__ void posenc_kernel(const float* __restrict__ x, int64_t n, int dims, int n_freqs, float* __restrict__ out) {
+    int width = dims * (1 + 2 * n_freqs);
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * width) return;
+    int64_t row = idx / width;
+    int j = (int)(idx - row * width);
+    float v;
+    if (j < dims) {
+        v = x[row * dims + j];
+    } else {
+        int q = (j - dims) / dims;           // 2*freq + (0: sin, 1: cos)
+        int c = (j - dims) - q * dims;
+        float a = __fmul_rn(x[row * dims + c], exp2f((float)(q >> 1)));   // 2^k scaling is exact
+        v = (q & 1) ? cosf(a) : sinf(a);
+    }
+    out[idx] = v;
+}
+
+extern "C" int inerf_posenc(const float* x, int64_t n, int dims, int n_freqs, float* out, void* stream) {
+    if (n < 0 || dims <= 0 || dims > 64 || n_freqs < 0 || n_freqs > 32)
+        return fail(INERF_E_SHAPE, "inerf_posenc: bad n/dims/n_freqs");
+    if (n == 0) return INERF_OK;
+    if (!x || !out) return fail(INERF_E_ARG, "inerf_posenc: NULL pointer");
+    int64_t total = n * dims * (1 + 2 * n_freqs);
+    if ((total + 255) / 256 > 0x7fffffffLL) return fail(INERF_E_SHAPE, "inerf_posenc: too many elements");
+    posenc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x, n, dims, n_freqs, out);
+    return check_launch("inerf_posenc");
+}
+
+// ---------------------------------------------------------------------------------------------
+// stratified coarse depths.  audio_exp_nerf.py:306-328
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float coarse_z(float near_, float far_, float t, int lindisp) {
+    if (!lindisp)   // near * (1. - t) + far * t
+        return __fadd_rn(__fmul_rn(near_, __fsub_rn(1.0f, t)), __fmul_rn(far_, t));
+    // 1. / (1. / near * (1. - t) + 1. / far * t)
+    float a = __fmul_rn(__fdiv_rn(1.0f, near_), __fsub_rn(1.0f, t));
+    float b = __fmul_rn(__fdiv_rn(1.0f, far_), t);
+    return __fdiv_rn(1.0f, __fadd_rn(a, b));
+}
+
+__global__ void sample_coarse_kernel(const float* __restrict__ rays, int n, int ray_stride, int s,
+                                     const float* __restrict__ t_vals, const float* __restrict__ t_rand, int lindisp,
+                                     float* __restrict__ z) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n * s) return;
+    int ray = (int)(idx / s);
+    int i = (int)(idx - (int64_t)ray * s);
+    float near_ = rays[(size_t)ray * ray_stride + 6], far_ = rays[(size_t)ray * ray_stride + 7];
+    float zi = coarse_z(near_, far_, t_vals[i], lindisp);
+    if (t_rand) {
+        // mids = .5*(z[1:]+z[:-1]); upper = [mids, z[-1]]; lower = [z[0], mids]; z = lower + (upper-lower)*r
+        float lo = zi, hi = zi;
+        if (i > 0) lo = __fmul_rn(0.5f, __fadd_rn(zi, coarse_z(near_, far_, t_vals[i - 1], lindisp)));
+        if (i < s - 1) hi = __fmul_rn(0.5f, __fadd_rn(coarse_z(near_, far_, t_vals[i + 1], lindisp), zi));
+        float r = (i == s - 1) ? 1.0f : t_rand[idx];       // t_rand[..., -1] = 1.0  (:326)
+        zi = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), r));
+    }
+    z[idx] = zi;
+}
+
+extern "C" int inerf_sample_coarse(const float* rays, int n, int ray_stride, int s, const float* t_vals,
+                                   const float* t_rand, int lindisp, float* z, void* stream) {
+    if (n < 0 || s <= 0 || s > 4096 || ray_stride < 8) return fail(INERF_E_SHAPE, "inerf_sample_coarse: bad n/s/stride");
+    if (n == 0) return INERF_OK;
+    if (!rays || !t_vals || !z) return fail(INERF_E_ARG, "inerf_sample_coarse: NULL pointer");
+    int64_t total = (int64_t)n * s;
+    sample_coarse_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(rays, n, ray_stride, s, t_vals,
+                                                                                        t_rand, lindisp, z);
+    return check_launch("inerf_sample_coarse");
+}
+
+// ---------------------------------------------------------------------------------------------
+// head/torso blend.  train_torso.py:269-270
+// ---------------------------------------------------------------------------------------------
+__global__ void blend_kernel(const float* __restrict__ rgb_head, const float* __restrict__ lw,
+                             const float* __restrict__ fg, int n, float* __restrict__ rgb) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * 3) return;
+    rgb[idx] = __fadd_rn(__fmul_rn(rgb_head[idx], lw[idx / 3]), fg[idx]);
+}
+
+extern "C" int inerf_head_torso_blend(const float* rgb_head, const float* last_weight_torso, const float* rgb_fg_torso,
+                                      int n, float* rgb, void* stream) {
+    if (n < 0) return fail(INERF_E_SHAPE, "inerf_head_torso_blend: n < 0");
+    if (n == 0) return INERF_OK;
+    if (!rgb_head || !last_weight_torso || !rgb_fg_torso || !rgb)
+        return fail(INERF_E_ARG, "inerf_head_torso_blend: NULL pointer");
+    blend_kernel<<<(n * 3 + 255) / 256, 256, 0, as_stream(stream)>>>(rgb_head, last_weight_torso, rgb_fg_torso, n, rgb);
+    return check_launch("inerf_head_torso_blend");
+}

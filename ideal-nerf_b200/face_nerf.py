@@ -1,0 +1,113 @@
+"""FaceNeRF: the audio/expression-conditioned NeRF MLP of models/face_nerf.py:8-80.
+
+Same constructor, same ``forward(x, aud, expr, latent_code)`` signature and -- because the layers are
+ordinary ``nn.Linear`` modules with the reference's attribute names -- the same ``state_dict`` keys
+(``pts_linears.0-7``, ``views_linears.0-2``, ``feature_linear``, ``alpha_linear``, ``rgb_linear``),
+so ``head.tar`` / ``*_torso.tar`` checkpoints load unchanged.  The arithmetic is one fused CUDA kernel
+(csrc/mlp_fp32.cu or csrc/mlp_bf16.cu) fed with the conditioning folded into biases.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+
+MODES = {"fp32": _lib.INERF_MLP_FP32, "bf16": _lib.INERF_MLP_BF16}
+
+
+class FaceNeRF(nn.Module):
+    def __init__(self, D=8, W=256, input_ch=63, input_ch_views=27, dim_aud=64, dim_latent=0, dim_expr=0,
+                 output_ch=4, skips=None, use_viewdirs=True, mlp_mode="fp32"):
+        super(FaceNeRF, self).__init__()
+        if skips is None:
+            skips = [4]
+        if not (D == 8 and W == 256 and input_ch == 63 and input_ch_views == 27 and list(skips) == [4]
+                and use_viewdirs):
+            raise NotImplementedError("ideal-nerf_b200 builds the configuration every reference script uses: "
+                                      "D=8, W=256, input_ch=63, input_ch_views=27, skips=[4], use_viewdirs=True")
+        self.D, self.W = D, W
+        self.input_xyz_ch, self.input_views_ch = input_ch, input_ch_views
+        self.dim_aud, self.dim_expr, self.dim_latent = dim_aud, dim_expr, dim_latent
+        self.skips, self.use_viewdirs = skips, use_viewdirs
+        self.mlp_mode = mlp_mode
+
+        input_ch_all = input_ch + dim_aud + dim_expr + dim_latent
+        self.pts_linears = nn.ModuleList(
+            [nn.Linear(input_ch_all, W)] + [nn.Linear(W, W) if i not in skips else nn.Linear(W + input_ch_all, W)
+                                            for i in range(D - 1)])
+        self.views_linears = nn.ModuleList([nn.Linear(input_ch_views + W + dim_expr, W // 2)] +
+                                           [nn.Linear(W // 2, W // 2) for _ in range(D // 4)])
+        self.feature_linear = nn.Linear(W, W)     # constructed, never applied (face_nerf.py:34) -- kept for checkpoints
+        self.alpha_linear = nn.Linear(W, 1)
+        self.rgb_linear = nn.Linear(W // 2, 3)
+        self._dims = ops.net_dims(dim_aud, dim_expr, dim_latent)
+        self._packed = None
+        self._packed_key = None
+
+    # -- plumbing -------------------------------------------------------------------------------
+    def kernel_params(self):
+        """The 26 tensors in include/inerf_b200.h order."""
+        ps = []
+        for l in self.pts_linears:
+            ps += [l.weight, l.bias]
+        for l in self.views_linears:
+            ps += [l.weight, l.bias]
+        ps += [self.alpha_linear.weight, self.alpha_linear.bias, self.rgb_linear.weight, self.rgb_linear.bias]
+        return ps
+
+    def _mode(self):
+        try:
+            return MODES[self.mlp_mode]
+        except KeyError:
+            raise ValueError(f"mlp_mode must be one of {sorted(MODES)}, got {self.mlp_mode!r}")
+
+    def packed_weights(self, params):
+        """Mode-specific packed weights, re-packed whenever a parameter was updated in place."""
+        mode = self._mode()
+        if mode == _lib.INERF_MLP_FP32:
+            return None
+        key = (mode, tuple((p.data_ptr(), p._version) for p in params))
+        if key != self._packed_key:
+            self._packed = ops.pack_weights(mode, self._dims, [p.detach() for p in params])
+            self._packed_key = key
+        return self._packed
+
+    def _prep(self, aud, expr, latent_code):
+        params = self.kernel_params()
+        for p in params:
+            if not p.is_cuda:
+                raise RuntimeError("FaceNeRF parameters must live on a CUDA device (no CPU path)")
+        if (aud is None) != (self.dim_aud == 0) or (expr is None) != (self.dim_expr == 0) \
+                or (latent_code is None) != (self.dim_latent == 0):
+            raise ValueError("aud/expr/latent_code must be given exactly for the non-zero dim_aud/dim_expr/dim_latent")
+        return params
+
+    # -- reference signature --------------------------------------------------------------------
+    def forward(self, x, aud, expr=None, latent_code=None):
+        """x (P, 63+27) already embedded, as in face_nerf.py:40.  Returns (P, 4) = [rgb, sigma] pre-activation."""
+        params = self._prep(aud, expr, latent_code)
+        return _MlpFn.apply(self, True, x, None, aud, expr, latent_code, *params)
+
+    # -- fused entry used by render_rays ----------------------------------------------------------
+    def query(self, rays, z_vals, aud, expr=None, latent_code=None):
+        """run_network on the points o + d*z of packed rays (n,11) / depths (n,s): returns raw (n,s,4)."""
+        params = self._prep(aud, expr, latent_code)
+        return _MlpFn.apply(self, False, rays, z_vals, aud, expr, latent_code, *params)
+
+
+class _MlpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, net, embedded, a, b, aud, expr, latent, *params):
+        mode = net._mode()
+        pd = [p.detach() for p in params]
+        cond = ops.fold_cond(net._dims, pd, aud, expr, latent)
+        packed = net.packed_weights(params)
+        if embedded:
+            out = ops.mlp_fwd_embedded(mode, net._dims, pd, packed, cond, a)
+        else:
+            out = ops.mlp_fwd(mode, net._dims, pd, packed, cond, a, b)
+        ctx.net = net
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        raise NotImplementedError("FaceNeRF backward kernels are not built yet (forward/render only)")

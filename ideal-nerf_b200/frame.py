@@ -1,0 +1,57 @@
+"""Full-frame driver around render_rays, with the frame's rays block-partitioned across GPUs.
+
+Reference: the per-frame loop of NeRFs/HeadNeRF/test/eval_aud_exp_nerf.py:485-495 (pose -> get_rays ->
+batchify_rays -> rgb) and the only multi-GPU code the reference has, nn.DataParallel over a ray
+re-shape (NeRFs/HeadNeRF/train/distribute_nerf.py:423,457-462).  Here: one process per GPU
+(torch.distributed), contiguous row bands of the image per rank, a full weight replica per rank, and
+ONE collective per frame -- the gather of the rendered bands (rays are independent: SURVEY.md 8e).
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .render import _render_rays_impl
+
+
+def band(n_rays, rank, world):
+    """Contiguous block [lo, hi) of rank `rank`; every rank gets ceil(n/world) rays except the tail."""
+    per = (n_rays + world - 1) // world
+    lo = min(n_rays, rank * per)
+    return lo, min(n_rays, lo + per)
+
+
+class FrameRenderer:
+    def __init__(self, network, rank=0, world=1, group=None):
+        self.net, self.rank, self.world, self.group = network, rank, world, group
+
+    def render_band(self, pose, aud, expr, latent, bc_rgb, perturb=0., lo=None, hi=None):
+        """Render this rank's rays of one H x W frame.  bc_rgb: (H*W,3) or (H,W,3) full background."""
+        n = self.net
+        H, W = n.H, n.W
+        rays = ops.get_rays_packed(H, W, n.focal, pose[:3, :4], n.near, n.far)
+        if lo is None:
+            lo, hi = band(H * W, self.rank, self.world)
+        bc = bc_rgb.reshape(-1, 3)[lo:hi]
+        ret = _render_rays_impl(rays[lo:hi], bc, n.face_nerf_coarse, n.face_nerf_fine, aud, expr, latent,
+                                n.args.N_samples, n.args.N_importance, perturb=perturb)
+        return ret, (lo, hi)
+
+    def gather_image(self, rgb_band, n_rays, dst=0):
+        """Assemble the (n_rays,3) image on rank `dst` from every rank's band (NCCL gather over NVLink)."""
+        if self.world == 1:
+            return rgb_band
+        per = (n_rays + self.world - 1) // self.world
+        if rgb_band.shape[0] < per:                                  # tail rank: pad to the common band size
+            pad = rgb_band.new_zeros((per - rgb_band.shape[0], 3))
+            rgb_band = torch.cat([rgb_band, pad], 0)
+        rgb_band = rgb_band.contiguous()
+        if self.rank == dst:
+            out = torch.empty((self.world * per, 3), device=rgb_band.device, dtype=rgb_band.dtype)
+            dist.gather(rgb_band, list(out.split(per, 0)), dst=dst, group=self.group)
+            return out[:n_rays]
+        dist.gather(rgb_band, None, dst=dst, group=self.group)
+        return None
+
+    def render_frame(self, pose, aud, expr, latent, bc_rgb, perturb=0.):
+        ret, _ = self.render_band(pose, aud, expr, latent, bc_rgb, perturb)
+        return self.gather_image(ret['rgb_map'], self.net.H * self.net.W)

@@ -1,0 +1,322 @@
+"""Tensor-level wrappers over the C ABI (include/inerf_b200.h) + autograd Functions.
+
+PyTorch supplies device memory, streams and autograd bookkeeping only; every op below is one
+hand-written CUDA kernel launched through ctypes on the current stream.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import InerfNetDims, ParamArray, check
+
+_tables = {}
+
+# ---- launch accounting (bench.py reads these; one entry per C-ABI kernel launch) -----------------
+LAUNCHES = {"count": 0}
+_timing = None          # None, or dict name -> list of (start_event, end_event)
+
+
+class kernel_timing:
+    """Context manager: record a CUDA-event pair around every kernel launch, on the launching stream."""
+
+    def __enter__(self):
+        global _timing
+        _timing = {}
+        return self
+
+    def __exit__(self, *exc):
+        global _timing
+        self.events, _timing = _timing, None
+        return False
+
+    def summary(self):
+        """name -> (launches, total_ms).  Call after a torch.cuda.synchronize()."""
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.events.items()}
+
+
+def call(name, fn, *args):
+    """Launch one C-ABI entry point: count it, optionally bracket it with events, raise on error."""
+    LAUNCHES["count"] += 1
+    if _timing is None:
+        check(fn(*args), name)
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    check(fn(*args), name)
+    b.record()
+    _timing.setdefault(name, []).append((a, b))
+
+
+def _need_cuda(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"ideal-nerf_b200: `{name}` must be a CUDA tensor (there is no CPU path)")
+
+
+def f32c(t, name="tensor"):
+    _need_cuda(t, name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def linspace_table(steps, device):
+    """torch.linspace(0,1,steps) evaluated on the CPU (the reference's bits), cached per device."""
+    key = (int(steps), str(device))
+    if key not in _tables:
+        _tables[key] = torch.linspace(0., 1., steps=int(steps)).to(device)
+    return _tables[key]
+
+
+# ------------------------------------------------------------------------------------------------
+# rays / encoding / coarse depths
+# ------------------------------------------------------------------------------------------------
+
+def get_rays_packed(H, W, focal, c2w, near, far, cx=None, cy=None):
+    """(H*W, 11) packed rays for a full frame.  helper.py:228-243 + audio_exp_nerf.py:409-427."""
+    c2w = f32c(c2w, "c2w")
+    if c2w.dim() != 2 or c2w.shape[0] < 3 or c2w.shape[1] != 4:
+        raise ValueError("c2w must be (3,4) or (4,4)")
+    cx = W * .5 if cx is None else cx
+    cy = H * .5 if cy is None else cy
+    rays = torch.empty((H * W, 11), device=c2w.device, dtype=torch.float32)
+    with torch.cuda.device(c2w.device):
+        call("inerf_get_rays", _lib.lib().inerf_get_rays, H, W, float(focal), float(cx), float(cy), ptr(c2w), 4, float(near), float(far),
+                                        ptr(rays), stream())
+    return rays
+
+
+def pack_rays(rays_o, rays_d, near, far):
+    rays_o = f32c(rays_o.reshape(-1, 3), "rays_o")
+    rays_d = f32c(rays_d.reshape(-1, 3), "rays_d")
+    n = rays_o.shape[0]
+    rays = torch.empty((n, 11), device=rays_o.device, dtype=torch.float32)
+    with torch.cuda.device(rays.device):
+        call("inerf_pack_rays", _lib.lib().inerf_pack_rays, ptr(rays_o), ptr(rays_d), n, float(near), float(far), ptr(rays), stream())
+    return rays
+
+
+def posenc(x, n_freqs):
+    x = f32c(x, "x")
+    dims = x.shape[-1]
+    flat = x.reshape(-1, dims)
+    out = torch.empty((flat.shape[0], dims * (1 + 2 * n_freqs)), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        call("inerf_posenc", _lib.lib().inerf_posenc, ptr(flat), flat.shape[0], dims, n_freqs, ptr(out), stream())
+    return out.reshape(*x.shape[:-1], out.shape[-1])
+
+
+def sample_coarse(rays, n_samples, t_rand=None, lindisp=False):
+    rays = f32c(rays, "rays")
+    n = rays.shape[0]
+    t_vals = linspace_table(n_samples, rays.device)
+    if t_rand is not None:
+        t_rand = f32c(t_rand, "t_rand")
+        assert t_rand.shape == (n, n_samples)
+    z = torch.empty((n, n_samples), device=rays.device, dtype=torch.float32)
+    with torch.cuda.device(rays.device):
+        call("inerf_sample_coarse", _lib.lib().inerf_sample_coarse, ptr(rays), n, rays.shape[1], n_samples, ptr(t_vals), ptr(t_rand),
+                                             int(bool(lindisp)), ptr(z), stream())
+    return z
+
+
+# ------------------------------------------------------------------------------------------------
+# compositing
+# ------------------------------------------------------------------------------------------------
+
+def _dir_view(rays_d):
+    """(pointer tensor, stride) for ray directions given either an (n,3) tensor or a column view of packed rays."""
+    _need_cuda(rays_d, "rays_d")
+    if rays_d.dtype == torch.float32 and rays_d.dim() == 2 and rays_d.shape[1] == 3 and rays_d.stride(1) == 1 \
+            and rays_d.stride(0) >= 3:
+        return rays_d, rays_d.stride(0)
+    d = f32c(rays_d.reshape(-1, 3), "rays_d")
+    return d, 3
+
+
+class _Composite(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, raw, z, rays_d, bc_rgb, noise, white_bkgd, with_fg):
+        raw, z, bc_rgb = f32c(raw, "raw"), f32c(z, "z_vals"), f32c(bc_rgb, "bc_rgb")
+        n, s = z.shape
+        assert raw.shape == (n, s, 4), f"raw {tuple(raw.shape)} vs z {tuple(z.shape)}"
+        d, ds = _dir_view(rays_d)
+        noise = f32c(noise, "noise") if noise is not None else None
+        dev = raw.device
+        rgb = torch.empty((n, 3), device=dev); disp = torch.empty((n,), device=dev)
+        acc = torch.empty((n,), device=dev); depth = torch.empty((n,), device=dev)
+        weights = torch.empty((n, s), device=dev)
+        fg = torch.empty((n, 3), device=dev) if with_fg else None
+        with torch.cuda.device(dev):
+            call("inerf_composite_fwd", _lib.lib().inerf_composite_fwd, ptr(raw), ptr(z), ptr(d), ds, ptr(bc_rgb), ptr(noise), n, s,
+                                                 int(bool(white_bkgd)), ptr(rgb), ptr(disp), ptr(acc), ptr(depth),
+                                                 ptr(weights), ptr(fg), stream())
+        ctx.save_for_backward(raw, z, d, bc_rgb, noise)
+        ctx.meta = (ds, int(bool(white_bkgd)), with_fg)
+        ctx.set_materialize_grads(False)
+        if with_fg:
+            return rgb, disp, acc, weights, depth, fg
+        return rgb, disp, acc, weights, depth
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_disp, g_acc, g_w, g_depth, g_fg=None):
+        raw, z, d, bc_rgb, noise = ctx.saved_tensors
+        ds, white, with_fg = ctx.meta
+        n, s = z.shape
+        gs = [None if g is None else f32c(g, "grad") for g in (g_rgb, g_disp, g_acc, g_depth, g_w, g_fg)]
+        d_raw = torch.empty_like(raw)
+        with torch.cuda.device(raw.device):
+            call("inerf_composite_bwd", _lib.lib().inerf_composite_bwd, ptr(raw), ptr(z), ptr(d), ds, ptr(bc_rgb), ptr(noise), n, s, white,
+                                                 ptr(gs[0]), ptr(gs[1]), ptr(gs[2]), ptr(gs[3]), ptr(gs[4]), ptr(gs[5]),
+                                                 ptr(d_raw), stream())
+        return d_raw, None, None, None, None, None, None
+
+
+def composite(raw, z, rays_d, bc_rgb, noise=None, white_bkgd=False, with_fg=False):
+    """raw2outputs.  Returns (rgb_map, disp_map, acc_map, weights, depth_map[, rgb_map_fg])."""
+    if z.shape[0] == 0:
+        n, s = z.shape
+        e = raw.new_zeros
+        out = (e((0, 3)), e((0,)), e((0,)), e((0, s)), e((0,)))
+        return out + (e((0, 3)),) if with_fg else out
+    return _Composite.apply(raw, z, rays_d, bc_rgb, noise, white_bkgd, with_fg)
+
+
+class _Blend(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rgb_head, lw, fg):
+        a, b, c = f32c(rgb_head, "rgb_head"), f32c(lw, "last_weight"), f32c(fg, "rgb_fg")
+        shape = a.shape
+        a2, c2 = a.reshape(-1, 3), c.reshape(-1, 3)
+        out = torch.empty_like(a2)
+        with torch.cuda.device(a.device):
+            call("inerf_head_torso_blend", _lib.lib().inerf_head_torso_blend, ptr(a2), ptr(b.reshape(-1)), ptr(c2), a2.shape[0], ptr(out),
+                                                    stream())
+        ctx.save_for_backward(a, b)
+        return out.reshape(shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors                 # three-term product rule of a 3-float-per-ray blend
+        return g * b[..., None], (g * a).sum(-1), g
+
+
+def head_torso_blend(rgb_head, last_weight_torso, rgb_fg_torso):
+    """rgb_head * last_weight_torso[..., None] + rgb_fg_torso   (train_torso.py:269-270)."""
+    return _Blend.apply(rgb_head, last_weight_torso, rgb_fg_torso)
+
+
+# ------------------------------------------------------------------------------------------------
+# importance sampling
+# ------------------------------------------------------------------------------------------------
+
+def sample_pdf_raw(bins, weights, u, policy=_lib.INERF_PDF_EXACT_TORCH_CPU, want_inds=False):
+    """helper.py:269-313.  u: (n_imp,) shared table or (n, n_imp) draws.  Returns (samples, inds|None)."""
+    bins, weights, u = f32c(bins, "bins"), f32c(weights, "weights"), f32c(u, "u")
+    n, nb = bins.shape
+    assert weights.shape == (n, nb - 1), "weights must be (n, n_bins-1)"
+    per_ray = int(u.dim() == 2)
+    n_imp = u.shape[-1]
+    zs = torch.empty((n, n_imp), device=bins.device)
+    inds = torch.empty((n, n_imp), device=bins.device, dtype=torch.int64) if want_inds else None
+    with torch.cuda.device(bins.device):
+        call("inerf_sample_pdf", _lib.lib().inerf_sample_pdf, ptr(bins), nb, ptr(weights), nb - 1, n, nb, n_imp, ptr(u), per_ray, policy,
+                                          ptr(zs), ptr(inds), None, 0, None, None, stream())
+    return zs, inds
+
+
+def importance_sample(z_coarse, w_coarse, u, policy=_lib.INERF_PDF_EXACT_TORCH_CPU, want_inds=False):
+    """Fused z_mid / weights[...,1:-1] / sample_pdf / sort(cat) / std of audio_exp_nerf.py:342-347,364.
+
+    Returns (z_samples, z_merged, z_std, inds|None); nothing here is differentiable (the reference detaches)."""
+    z_coarse, w_coarse, u = f32c(z_coarse.detach(), "z_vals"), f32c(w_coarse.detach(), "weights"), f32c(u, "u")
+    n, s1 = z_coarse.shape
+    per_ray = int(u.dim() == 2)
+    n_imp = u.shape[-1]
+    dev = z_coarse.device
+    zs = torch.empty((n, n_imp), device=dev)
+    zm = torch.empty((n, s1 + n_imp), device=dev)
+    zstd = torch.empty((n,), device=dev)
+    inds = torch.empty((n, n_imp), device=dev, dtype=torch.int64) if want_inds else None
+    with torch.cuda.device(dev):
+        call("inerf_importance_sample", _lib.lib().inerf_importance_sample, ptr(z_coarse), ptr(w_coarse), n, s1, n_imp, ptr(u), per_ray, policy,
+                                                 ptr(zs), ptr(inds), ptr(zm), ptr(zstd), stream())
+    return zs, zm, zstd, inds
+
+
+# ------------------------------------------------------------------------------------------------
+# FaceNeRF MLP
+# ------------------------------------------------------------------------------------------------
+
+def net_dims(dim_aud, dim_expr, dim_latent):
+    return InerfNetDims(int(dim_aud), int(dim_expr), int(dim_latent), 256, 8, 63, 27)
+
+
+def param_array(params):
+    """ctypes array of the 26 device pointers in include/inerf_b200.h order (tensors must stay alive)."""
+    assert len(params) == _lib.N_PARAMS
+    arr = ParamArray()
+    for i, p in enumerate(params):
+        _need_cuda(p, "parameter")
+        assert p.dtype == torch.float32 and p.is_contiguous()
+        arr[i] = p.data_ptr()
+    return arr
+
+
+def fold_cond(dims, params, aud, expr, latent):
+    n = ctypes.c_size_t()
+    check(_lib.lib().inerf_mlp_cond_floats(ctypes.byref(dims), ctypes.byref(n)), "inerf_mlp_cond_floats")
+    dev = params[0].device
+    cond = torch.empty((n.value,), device=dev)
+    aud = f32c(aud, "aud") if dims.dim_aud > 0 else None
+    expr = f32c(expr, "expr") if dims.dim_expr > 0 else None
+    latent = f32c(latent, "latent_code") if dims.dim_latent > 0 else None
+    arr = param_array(params)
+    with torch.cuda.device(dev):
+        call("inerf_mlp_fold_cond", _lib.lib().inerf_mlp_fold_cond, ctypes.byref(dims), arr, ptr(aud), ptr(expr), ptr(latent), ptr(cond),
+                                             stream())
+    return cond
+
+
+def pack_weights(mode, dims, params):
+    nb = ctypes.c_size_t()
+    check(_lib.lib().inerf_mlp_packed_bytes(mode, ctypes.byref(dims), ctypes.byref(nb)), "inerf_mlp_packed_bytes")
+    if nb.value == 0:
+        return None
+    dev = params[0].device
+    packed = torch.empty((nb.value,), device=dev, dtype=torch.uint8)
+    arr = param_array(params)
+    with torch.cuda.device(dev):
+        call("inerf_mlp_pack", _lib.lib().inerf_mlp_pack, mode, ctypes.byref(dims), arr, ptr(packed), stream())
+    return packed
+
+
+def mlp_fwd(mode, dims, params, packed, cond, rays, z):
+    """run_network for one pass (points, gamma(p), gamma(v), FaceNeRF).  rays (n,11), z (n,s) -> raw (n,s,4)."""
+    rays, z = f32c(rays, "rays"), f32c(z, "z_vals")
+    n, s = z.shape
+    raw = torch.empty((n, s, 4), device=z.device)
+    arr = param_array(params)
+    with torch.cuda.device(z.device):
+        call("inerf_mlp_fwd", _lib.lib().inerf_mlp_fwd, mode, ctypes.byref(dims), arr, ptr(packed), ptr(cond), ptr(rays), rays.shape[1],
+                                       ptr(z), n, s, ptr(raw), stream())
+    return raw
+
+
+def mlp_fwd_embedded(mode, dims, params, packed, cond, x):
+    x = f32c(x, "x")
+    assert x.dim() == 2 and x.shape[1] == 90, "x must be (P, 63+27)"
+    out = torch.empty((x.shape[0], 4), device=x.device)
+    arr = param_array(params)
+    with torch.cuda.device(x.device):
+        call("inerf_mlp_fwd_embedded", _lib.lib().inerf_mlp_fwd_embedded, mode, ctypes.byref(dims), arr, ptr(packed), ptr(cond), ptr(x),
+                                                x.shape[0], ptr(out), stream())
+    return out

@@ -1,0 +1,189 @@
+/*
+ * inerf_b200.h -- C ABI of the B200-native IDEAL-NeRF render_rays hot path.
+ *
+ * The reference (GaryGky/IDEAL-NeRF) has no FFI: its boundary is the Python call surface of
+ * NeRFs/HeadNeRF/train/audio_exp_nerf.py (Network.render_rays and friends), NeRFs/HeadNeRF/helper.py,
+ * NeRFs/HeadNeRF/train/baseline.py and models/face_nerf.py.  Every entry point below replaces one
+ * stage of that surface and cites the reference lines it stands in for.  The Python package
+ * `ideal-nerf_b200/` keeps the reference's names and signatures and calls these through ctypes
+ * (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - plain C, POD arguments only; every pointer is a DEVICE pointer to contiguous row-major fp32
+ *     unless the name ends in `_host` or the comment says otherwise;
+ *   - `stream` is a cudaStream_t passed as void*; entry points only enqueue work, they never
+ *     synchronise, allocate or free device memory;
+ *   - return 0 on success, a negative INERF_E_* on bad arguments, a positive cudaError_t when the
+ *     CUDA runtime reports a launch error; inerf_last_error() gives the message (thread local);
+ *   - re-entrant per (device, stream); no global mutable state besides the last-error string.
+ */
+#ifndef INERF_B200_H
+#define INERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define INERF_VERSION 100 /* 0.1.0 */
+
+enum {
+    INERF_OK = 0,
+    INERF_E_ARG = -1,         /* null pointer / negative size */
+    INERF_E_SHAPE = -2,       /* size outside what the kernels support */
+    INERF_E_ALIGN = -3,       /* pointer not aligned as required */
+    INERF_E_UNSUPPORTED = -4, /* mode / dims not built */
+    INERF_E_DEVICE = -5       /* current device is not sm_100 */
+};
+
+/* MLP arithmetic modes (north_star: fp32 gate <= 1e-3 max-abs, bf16-MLP gate <= 0.05 dB PSNR) */
+enum {
+    INERF_MLP_FP32 = 0, /* fp32 FFMA, weights read in nn.Linear layout                         */
+    INERF_MLP_BF16 = 1  /* bf16 operands, fp32 accumulate in TMEM, tcgen05.mma (packed weights) */
+};
+
+/* sample_pdf summation policies */
+enum {
+    INERF_PDF_EXACT_TORCH_CPU = 0, /* bit-reproduces torch.sum / torch.cumsum on CPU (the oracle) */
+    INERF_PDF_FAST = 1             /* warp-shuffle fp32 sum                                       */
+};
+
+/* FaceNeRF geometry, models/face_nerf.py:9-36.  Only D=8, W=256, skips=[4], in_xyz=63,
+ * in_views=27, use_viewdirs=True (the configuration every reference script builds) is supported. */
+typedef struct InerfNetDims {
+    int32_t dim_aud;    /* 64 head; 106 torso (train_torso.py:213-221) */
+    int32_t dim_expr;   /* 76 head (79 in train_torso.py:203); 0 torso */
+    int32_t dim_latent; /* 32 head; 0 torso                             */
+    int32_t width;      /* 256 */
+    int32_t depth;      /* 8   */
+    int32_t in_xyz;     /* 63  */
+    int32_t in_views;   /* 27  */
+} InerfNetDims;
+
+/* Parameter pointers of one FaceNeRF in state_dict order (models/face_nerf.py:27-36):
+ *   [0..15]  pts_linears.{0..7}.{weight,bias}
+ *   [16..21] views_linears.{0..2}.{weight,bias}
+ *   [22,23]  alpha_linear.{weight,bias}
+ *   [24,25]  rgb_linear.{weight,bias}
+ * feature_linear is never applied by the reference forward (face_nerf.py:34) and is not passed.
+ * The array itself lives in HOST memory; its entries are DEVICE pointers (nn.Linear layout, (out,in)). */
+#define INERF_N_PARAMS 26
+
+int inerf_version(void);
+const char* inerf_last_error(void);
+/* 0 when the current CUDA device is compute capability 10.x, INERF_E_DEVICE otherwise. */
+int inerf_device_check(void);
+
+/* ---- rays ----------------------------------------------------------------------------------- */
+
+/* get_rays + ray packing for a full HxW frame.
+ * Replaces helper.py:228-243 (get_rays) followed by audio_exp_nerf.py:409-427 (viewdirs, near/far
+ * columns).  c2w: device, 3 rows of 4 floats with `c2w_row_stride` floats between rows.
+ * rays: (H*W, 11) = [o(3), d(3), near, far, d/|d|(3)]. */
+int inerf_get_rays(int H, int W, float focal, float cx, float cy, const float* c2w, int c2w_row_stride,
+                   float near_, float far_, float* rays, void* stream);
+
+/* Ray packing from caller-supplied origins/directions (training batches).
+ * Replaces audio_exp_nerf.py:409-427.  rays_o, rays_d: (n,3); rays: (n,11). */
+int inerf_pack_rays(const float* rays_o, const float* rays_d, int n, float near_, float far_, float* rays,
+                    void* stream);
+
+/* Positional encoding gamma(x) = [x, sin(2^0 x), cos(2^0 x), ..., sin(2^(L-1) x), cos(2^(L-1) x)].
+ * Replaces helper.py:174-224 (Embedder.embed via get_embedder).  x: (n, dims), out: (n, dims*(1+2L)). */
+int inerf_posenc(const float* x, int64_t n, int dims, int n_freqs, float* out, void* stream);
+
+/* Stratified coarse depths.  Replaces audio_exp_nerf.py:306-328 (baseline.py:385-410).
+ * rays: (n, ray_stride) with near/far in columns 6,7.  t_vals: (s) = torch.linspace(0,1,s) (a host
+ * generated table -- SURVEY.md 7-1).  t_rand: NULL (perturb == 0) or (n, s) uniform draws; the last
+ * column is forced to 1.0 as the reference does at :326.  z: (n, s). */
+int inerf_sample_coarse(const float* rays, int n, int ray_stride, int s, const float* t_vals,
+                        const float* t_rand, int lindisp, float* z, void* stream);
+
+/* ---- compositing ---------------------------------------------------------------------------- */
+
+/* raw2outputs forward.  Replaces baseline.py:325-375 and, with rgb_fg != NULL, the torso variant
+ * test_torso.py:352-402.
+ * raw (n,s,4) [r,g,b,sigma] pre-activation; z (n,s); rays_d: pointer to the first direction with
+ * `rays_d_stride` floats between rays (3 for an (n,3) tensor, 11 for rays+3); bc_rgb (n,3);
+ * noise: NULL or (n,s) already scaled by raw_noise_std.
+ * Outputs: rgb (n,3), disp (n), acc (n), depth (n), weights (n,s), rgb_fg (n,3) or NULL. */
+int inerf_composite_fwd(const float* raw, const float* z, const float* rays_d, int rays_d_stride,
+                        const float* bc_rgb, const float* noise, int n, int s, int white_bkgd, float* rgb,
+                        float* disp, float* acc, float* depth, float* weights, float* rgb_fg, void* stream);
+
+/* raw2outputs backward (the reference's is autograd of baseline.py:339-375).
+ * Any of the incoming gradients may be NULL (treated as zero).  Writes d_raw (n,s,4). */
+int inerf_composite_bwd(const float* raw, const float* z, const float* rays_d, int rays_d_stride,
+                        const float* bc_rgb, const float* noise, int n, int s, int white_bkgd,
+                        const float* g_rgb, const float* g_disp, const float* g_acc, const float* g_depth,
+                        const float* g_weights, const float* g_rgb_fg, float* d_raw, void* stream);
+
+/* Head/torso blend rgb = rgb_head * last_weight_torso[:,None] + rgb_fg_torso.
+ * Replaces train_torso.py:269-270 / test_torso.py:523. */
+int inerf_head_torso_blend(const float* rgb_head, const float* last_weight_torso, const float* rgb_fg_torso,
+                           int n, float* rgb, void* stream);
+
+/* ---- importance sampling -------------------------------------------------------------------- */
+
+/* sample_pdf.  Replaces helper.py:269-313.
+ * bins: (n, n_bins) with row stride bins_stride; weights: (n, n_bins-1) with row stride w_stride
+ * (so weights[...,1:-1] of an (n,S) tensor is passed as w+1 with stride S).
+ * u: n_imp floats shared by every ray when u_per_ray == 0 (torch.linspace(0,1,n_imp) for det=True),
+ * else (n, n_imp) draws.  z_samples (n, n_imp); inds: NULL or (n, n_imp) int64 =
+ * torch.searchsorted(cdf, u, right=True).
+ * Optional fused tail of render_rays (audio_exp_nerf.py:347,364): when z_coarse != NULL (n, s1),
+ * z_merged (n, s1+n_imp) = sort(cat(z_coarse, z_samples)) and z_std (n) = std(z_samples, unbiased=False). */
+int inerf_sample_pdf(const float* bins, int bins_stride, const float* weights, int w_stride, int n, int n_bins,
+                     int n_imp, const float* u, int u_per_ray, int policy, float* z_samples, int64_t* inds,
+                     const float* z_coarse, int s1, float* z_merged, float* z_std, void* stream);
+
+/* Fused form used by render_rays: bins = mid-points of z_coarse, weights = w_coarse[:,1:-1]
+ * (audio_exp_nerf.py:342-347).  z_coarse, w_coarse: (n, s1). */
+int inerf_importance_sample(const float* z_coarse, const float* w_coarse, int n, int s1, int n_imp,
+                            const float* u, int u_per_ray, int policy, float* z_samples, int64_t* inds,
+                            float* z_merged, float* z_std, void* stream);
+
+/* ---- FaceNeRF MLP --------------------------------------------------------------------------- */
+
+/* Number of floats of the per-call conditioning buffer written by inerf_mlp_fold_cond. */
+int inerf_mlp_cond_floats(const InerfNetDims* dims, size_t* n_floats);
+
+/* Fold the per-call constant conditioning columns into biases:
+ *   b0'  = b0  + W0[:,63:]            . [aud | expr/3 | latent]
+ *   b5'  = b5  + W5[:,63:63+cond]     . [aud | expr/3 | latent]
+ *   bV0' = bV0 + WV0[:,283:283+expr]  . expr/3
+ * Replaces the three einops.repeat + torch.cat of face_nerf.py:44-56,69 (and `expr * 1 / 3`, :49).
+ * params_host: INERF_N_PARAMS device pointers (host array).  aud/expr/latent may be NULL when the
+ * corresponding dim is 0.  cond: device buffer of inerf_mlp_cond_floats floats holding every bias
+ * of the folded network: [b0'(W) b1..b4 b5' b6 b7 | bV0'(W/2) bV1 bV2 | alpha_b(1) rgb_b(3)]. */
+int inerf_mlp_fold_cond(const InerfNetDims* dims, const float* const* params_host, const float* aud,
+                        const float* expr, const float* latent, float* cond, void* stream);
+
+/* Bytes of the packed-weight blob for `mode` (0 for INERF_MLP_FP32, which reads nn.Linear layout). */
+int inerf_mlp_packed_bytes(int mode, const InerfNetDims* dims, size_t* bytes);
+
+/* Re-lay the per-point weights for `mode` (bf16, K-major 128B-swizzled UMMA tiles in MMA issue
+ * order).  Re-run after every optimiser step. */
+int inerf_mlp_pack(int mode, const InerfNetDims* dims, const float* const* params_host, void* packed,
+                   void* stream);
+
+/* run_network for one pass: points p = o + d*z, gamma_10(p), gamma_4(viewdir), FaceNeRF.
+ * Replaces audio_exp_nerf.py:332 + :376-394 + face_nerf.py:40-80 (positional encoding fused into the
+ * first-layer operand; no (P,90) tensor is materialised).
+ * rays (n, ray_stride) as produced by inerf_get_rays/inerf_pack_rays; z (n, s); raw (n, s, 4). */
+int inerf_mlp_fwd(int mode, const InerfNetDims* dims, const float* const* params_host, const void* packed,
+                  const float* cond, const float* rays, int ray_stride, const float* z, int n, int s,
+                  float* raw, void* stream);
+
+/* FaceNeRF.forward on already-embedded inputs x (p, in_xyz+in_views) -- the reference module's own
+ * call signature (face_nerf.py:40).  out (p, 4). */
+int inerf_mlp_fwd_embedded(int mode, const InerfNetDims* dims, const float* const* params_host,
+                           const void* packed, const float* cond, const float* x, int64_t p, float* out,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INERF_B200_H */

@@ -1,0 +1,373 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the committed
+golden outputs of the unmodified reference.  Run by the driver with ``-m gpu`` on a real B200.
+
+Tolerances (BASELINE.json north_star):
+  * sample_pdf indices: bit-exact (policy EXACT_TORCH_CPU, fp32, det=True and with supplied draws);
+    the samples themselves are compared bit-exact too;
+  * stratified depths / merged depths: bit-exact;
+  * fp32 MLP mode: rgb / depth / acc max-abs <= 1e-3 end to end (measured ~1e-5; asserted at 1e-4
+    where the golden comparison allows it);
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import render_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def M():
+    import ideal_nerf_b200 as m
+    assert torch.cuda.is_available(), "-m gpu tests need a GPU"
+    m.lib()                                       # raises if the extension is missing: no fallback
+    from ideal_nerf_b200 import _lib
+    _lib.check(m.lib().inerf_device_check(), "inerf_device_check")
+    return m
+
+
+def C(a):
+    return torch.as_tensor(np.asarray(a)).to(DEV)
+
+
+def maxabs(a, b):
+    a = a.detach().cpu().double().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, np.float64)
+    b = b.detach().cpu().double().numpy() if isinstance(b, torch.Tensor) else np.asarray(b, np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.max(np.abs(a - b))) if a.size else 0.0
+
+
+def close(a, b, tol, what=""):
+    e = maxabs(a, b)
+    assert e <= tol, f"{what}: max-abs {e:.3e} > {tol:.1e}"
+
+
+def bits_equal(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a,
+                                                 b.view(np.uint32) if b.dtype == np.float32 else b)
+
+
+def head_net(M, sd, mode="fp32", **kw):
+    net = M.FaceNeRF(dim_aud=kw.get("dim_aud", 64), dim_latent=kw.get("dim_latent", 32),
+                     dim_expr=kw.get("dim_expr", 76), mlp_mode=mode)
+    net.load_state_dict(sd)
+    return net.to(DEV)
+
+
+# ------------------------------------------------------------------------------------------------
+# rays, encoding, coarse depths
+# ------------------------------------------------------------------------------------------------
+def test_get_rays_and_embed(M, golden):
+    g = golden("rays_embed")
+    ro, rd = M.get_rays(6, 5, 9.5, C(g["c2w"]))
+    close(ro, g["rays_o"], 0, "rays_o"); close(rd, g["rays_d"], 1e-7, "rays_d")
+    ro, rd = M.get_rays(6, 5, 9.5, C(g["c2w"]), 2.25, 3.5)
+    close(rd, g["rays_d_c"], 1e-7, "rays_d cx,cy")
+    cam = O.synthetic_camera()
+    ro, rd = M.get_rays(cam["H"], cam["W"], cam["focal"], cam["c2w"].to(DEV), cam["cx"], cam["cy"])
+    close(rd.reshape(-1, 3)[C(g["frame_pick"])], g["frame_rays_d"], 1e-7, "frame rays_d")
+    close(rd.double().sum((0, 1)), g["frame_rays_d_sum"], 1e-2, "frame rays_d checksum")
+    e10, d10 = M.get_embedder(10, 0)
+    e4, d4 = M.get_embedder(4, 0)
+    assert (d10, d4) == (63, 27)
+    close(e10(C(g["x"])), g["embed10"], 5e-6, "embed10")       # |2^9 x| ~ 300 rad: 1 ulp of the argument ~ 3e-5
+    close(e4(C(g["x"])), g["embed4"], 1e-6, "embed4")
+
+
+def test_packed_rays_match_oracle(M):
+    fr = O.synthetic_frame(0)
+    cam = O.synthetic_camera()
+    packed = M.ops.get_rays_packed(cam["H"], cam["W"], cam["focal"], cam["c2w"].to(DEV), O.NEAR, O.FAR, cam["cx"], cam["cy"])
+    close(packed, fr["rays"], 2e-7, "packed rays (frame)")
+    ro, rd = fr["rays"][:777, 0:3], fr["rays"][:777, 3:6]
+    close(M.ops.pack_rays(ro.to(DEV), rd.to(DEV), O.NEAR, O.FAR), fr["rays"][:777], 1e-7, "pack_rays")
+
+
+@pytest.mark.parametrize("lindisp", [False, True])
+def test_stratified_depths_bit_exact(M, lindisp):
+    b = O.synthetic_train_batch(0)
+    rays = b["rays"][:301]
+    near, far = rays[:, 6:7], rays[:, 7:8]
+    z = M.ops.sample_coarse(rays.to(DEV), 64, None, lindisp)
+    assert bits_equal(z, O.stratified_z(near, far, 64, 301, None, lindisp))
+    t_rand = torch.rand(301, 64, generator=torch.Generator().manual_seed(4))
+    z = M.ops.sample_coarse(rays.to(DEV), 64, t_rand.to(DEV), lindisp)
+    assert bits_equal(z, O.stratified_z(near, far, 64, 301, t_rand, lindisp))
+    z7 = M.ops.sample_coarse(rays.to(DEV), 7, None, lindisp)                    # ragged / tiny S
+    assert bits_equal(z7, O.stratified_z(near, far, 7, 301, None, lindisp))
+    assert M.ops.sample_coarse(rays[:0].to(DEV), 64).shape == (0, 64)          # empty
+
+
+# ------------------------------------------------------------------------------------------------
+# compositing
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["s64", "s192", "s7"])
+def test_raw2outputs_golden(M, golden, tag):
+    g = golden("raw2outputs")
+    a = [C(g[f"{tag}_{k}"]) for k in ("raw", "z", "d", "bc")]
+    rgb, disp, acc, w, depth = M.raw2outputs(*a)
+    close(rgb, g[f"{tag}_rgb"], 2e-6, "rgb"); close(acc, g[f"{tag}_acc"], 2e-6, "acc")
+    close(w, g[f"{tag}_w"], 2e-6, "weights"); close(depth, g[f"{tag}_depth"], 2e-6, "depth")
+    close(disp, g[f"{tag}_disp"], 1e-5, "disp")
+    t = M.raw2outputs_torso(*a)
+    close(t[5], g[f"{tag}_rgb_fg"], 2e-6, "rgb_fg"); close(t[0], g[f"{tag}_torso_rgb"], 2e-6, "torso rgb")
+    close(M.raw2outputs(*a, white_bkgd=True)[0], g[f"{tag}_rgb_white"], 2e-6, "white_bkgd")
+    rn = M.raw2outputs(*a, raw_noise_std=0.5, pytest=True)
+    close(rn[0], g[f"{tag}_rgb_noise"], 2e-6, "noise rgb"); close(rn[3], g[f"{tag}_w_noise"], 2e-6, "noise w")
+
+
+def test_raw2outputs_strided_dirs_and_empty(M, golden):
+    g = golden("raw2outputs")
+    n = g["s64_raw"].shape[0]
+    rays = torch.zeros(n, 11)
+    rays[:, 3:6] = torch.from_numpy(g["s64_d"])
+    rays = rays.to(DEV)
+    rgb = M.raw2outputs(C(g["s64_raw"]), C(g["s64_z"]), rays[:, 3:6], C(g["s64_bc"]))[0]     # stride-11 view
+    close(rgb, g["s64_rgb"], 2e-6, "strided rays_d")
+    e = M.raw2outputs(torch.zeros(0, 64, 4, device=DEV), torch.zeros(0, 64, device=DEV),
+                      torch.zeros(0, 3, device=DEV), torch.zeros(0, 3, device=DEV))
+    assert e[0].shape == (0, 3) and e[3].shape == (0, 64)
+
+
+def test_raw2outputs_backward_golden(M, golden):
+    g = golden("raw2outputs")
+    raw = C(g["s64_raw"][:48]).clone().requires_grad_(True)
+    t = M.raw2outputs_torso(raw, C(g["s64_z"][:48]), C(g["s64_d"][:48]), C(g["s64_bc"][:48]))
+    ((t[0] * C(g["bwd_g_rgb"])).sum() + (t[5] * C(g["bwd_g_fg"])).sum() + (t[3] * C(g["bwd_g_w"])).sum()
+     + (t[2] * C(g["bwd_g_acc"])).sum() + (t[4] * C(g["bwd_g_depth"])).sum() + (t[1] * C(g["bwd_g_disp"])).sum()).backward()
+    close(raw.grad, g["bwd_d_raw"], 1e-5, "d_raw")
+
+
+@pytest.mark.parametrize("s,white", [(64, False), (192, True), (33, False), (257, False)])
+def test_raw2outputs_backward_vs_oracle_autograd(M, s, white):
+    gen = torch.Generator().manual_seed(s)
+    n = 70
+    raw = torch.randn(n, s, 4, generator=gen) * torch.tensor([2., 2., 2., 5.])
+    z = torch.sort(O.NEAR + 0.6 * torch.rand(n, s, generator=gen), -1)[0]
+    d = torch.randn(n, 3, generator=gen) * 0.1 + torch.tensor([0., 0., -1.])
+    bc = torch.rand(n, 3, generator=gen)
+    gs = [torch.randn(n, 3, generator=gen), torch.randn(n, generator=gen) * 0.1, torch.randn(n, generator=gen),
+          torch.randn(n, s, generator=gen), torch.randn(n, generator=gen), torch.randn(n, 3, generator=gen)]
+    r0 = raw.clone().requires_grad_(True)
+    o = O.raw2outputs(r0, z, d, bc, white_bkgd=white, with_fg=True)
+    sum((a * b).sum() for a, b in zip(o, gs)).backward()
+    r1 = raw.to(DEV).requires_grad_(True)
+    t = M.ops.composite(r1, z.to(DEV), d.to(DEV), bc.to(DEV), None, white, True)
+    for a, b in zip(t, o):
+        close(a, b, 3e-6 if a.dim() else 3e-6, "fwd")
+    sum((a * b.to(DEV)).sum() for a, b in zip(t, gs)).backward()
+    close(r1.grad, r0.grad, 2e-5 * max(1.0, float(r0.grad.abs().max())), "d_raw vs autograd")
+
+
+# ------------------------------------------------------------------------------------------------
+# importance sampling
+# ------------------------------------------------------------------------------------------------
+def test_sample_pdf_indices_bit_exact(M, golden):
+    g = golden("sample_pdf")
+    bins, w = C(g["bins"]), C(g["weights"])
+    u = torch.linspace(0., 1., 128).to(DEV)
+    zs, inds = M.ops.sample_pdf_raw(bins, w, u, want_inds=True)
+    assert np.array_equal(inds.cpu().numpy(), g["inds_det"].astype(np.int64)), "det indices differ from the reference"
+    assert bits_equal(zs, g["samples_det"]), "det samples differ in bits"
+    zs, inds = M.ops.sample_pdf_raw(bins, w, C(g["u_rnd"]), want_inds=True)
+    assert np.array_equal(inds.cpu().numpy(), g["inds_rnd"].astype(np.int64)), "random-u indices differ"
+    assert bits_equal(zs, g["samples_rnd"])
+    # reference-signature wrapper
+    assert bits_equal(M.sample_pdf(bins, w, 128, det=True), g["samples_det"])
+    assert bits_equal(M.sample_pdf(bins, w, 128, det=False, pytest=True), g["samples_rnd"])
+
+
+def test_sample_pdf_indices_on_render_weights(M, golden):
+    """All 3072 rays of the synthetic batch, weights produced by the reference's own coarse pass."""
+    g = golden("render_3072")
+    b = O.synthetic_train_batch(0)
+    z = O.stratified_z(b["rays"][:, 6:7], b["rays"][:, 7:8], 64, 3072)
+    mid = .5 * (z[:, 1:] + z[:, :-1])
+    for tag in ("init", "dense"):
+        w0 = g[f"{tag}_w0_all"]
+        u = torch.linspace(0., 1., 128)
+        s_ref, i_ref, _ = O.sample_pdf_exact(mid.numpy(), w0[:, 1:-1], u.numpy())
+        assert np.array_equal(s_ref, g[f"{tag}_zs_all"]), "oracle restatement drifted from the reference output"
+        zs, zm, zstd, inds = M.ops.importance_sample(z.to(DEV), C(w0), u.to(DEV), want_inds=True)
+        assert np.array_equal(inds.cpu().numpy(), i_ref), f"{tag}: indices differ"
+        assert bits_equal(zs, g[f"{tag}_zs_all"]), f"{tag}: samples differ in bits"
+        ref_sorted = torch.sort(torch.cat([z, torch.from_numpy(g[f"{tag}_zs_all"])], -1), -1)[0]
+        assert bits_equal(zm, ref_sorted), f"{tag}: merged depths differ"
+        close(zstd, torch.std(torch.from_numpy(g[f"{tag}_zs_all"]), -1, unbiased=False), 1e-6, "z_std")
+
+
+@pytest.mark.parametrize("nb,n_imp", [(63, 128), (31, 64), (15, 7), (127, 200), (9, 1)])
+def test_sample_pdf_shapes_vs_oracle(M, nb, n_imp):
+    gen = torch.Generator().manual_seed(nb * 1000 + n_imp)
+    n = 257
+    bins = torch.sort(torch.rand(n, nb, generator=gen), -1)[0]
+    w = torch.rand(n, nb - 1, generator=gen) ** 3
+    w[:5] = 0.
+    u = torch.rand(n, n_imp, generator=gen)
+    s_ref, i_ref, _ = O.sample_pdf_exact(bins.numpy(), w.numpy(), u.numpy())
+    zs, inds = M.ops.sample_pdf_raw(bins.to(DEV), w.to(DEV), u.to(DEV), want_inds=True)
+    assert np.array_equal(inds.cpu().numpy(), i_ref)
+    assert bits_equal(zs, s_ref)
+    zs_fast, _ = M.ops.sample_pdf_raw(bins.to(DEV), w.to(DEV), u.to(DEV), policy=M._lib.INERF_PDF_FAST)
+    close(zs_fast, s_ref, 1e-4, "FAST policy samples")          # an index flip moves a sample by ~1 ulp of a bin edge
+
+
+def test_importance_sample_full_frame_properties(M):
+    """BASELINE size (202 500 rays): size-independent properties of the merged depths."""
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    n = 202500
+    fr = O.synthetic_frame(0)
+    rays = fr["rays"].to(DEV)
+    z = M.ops.sample_coarse(rays, 64, torch.rand(n, 64, device=DEV, generator=gen))
+    w = torch.rand(n, 64, device=DEV, generator=gen) ** 4
+    u = torch.rand(n, 128, device=DEV, generator=gen)
+    zs, zm, zstd, inds = M.ops.importance_sample(z, w, u, want_inds=True)
+    assert zm.shape == (n, 192) and bool((zm[:, 1:] >= zm[:, :-1]).all()), "merged depths must be sorted"
+    assert bool((inds >= 1).all()) and bool((inds <= 63).all())
+    mid_lo, mid_hi = .5 * (z[:, 0] + z[:, 1]), .5 * (z[:, -1] + z[:, -2])
+    assert bool((zs >= mid_lo[:, None]).all()) and bool((zs <= mid_hi[:, None]).all())
+    ref = torch.sort(torch.cat([z, zs], -1), -1)[0]
+    assert torch.equal(zm, ref), "merge must equal sort(cat)"
+    close(zstd, torch.std(zs, -1, unbiased=False), 2e-6, "z_std")
+    assert torch.equal(zm.sum(-1, dtype=torch.float64), ref.sum(-1, dtype=torch.float64))   # checksum
+
+
+# ------------------------------------------------------------------------------------------------
+# FaceNeRF
+# ------------------------------------------------------------------------------------------------
+def test_face_nerf_forward_golden(M, golden):
+    g = golden("face_nerf")
+    net = head_net(M, O.init_face_nerf(int(g["seed_head"])))
+    with torch.no_grad():
+        out = net(C(g["x"]), C(g["aud"]), C(g["expr"]), C(g["latent"]))
+    close(out, g["out_head"], 2e-5, "FaceNeRF head")
+    net_t = head_net(M, O.init_face_nerf(int(g["seed_torso"]), 106, 0, 0), dim_aud=106, dim_latent=0, dim_expr=0)
+    with torch.no_grad():
+        out = net_t(C(g["x"]), C(g["aud_torso"]))
+    close(out, g["out_torso"], 2e-5, "FaceNeRF torso")
+    assert set(net.state_dict()) == set(O.init_face_nerf(1)), "state_dict keys must equal the reference's"
+
+
+def test_face_nerf_fused_query_matches_embedded(M):
+    """Fused PE path (rays, z) against the embedded-input path on the same points, ragged tile (n*s % 64 != 0)."""
+    b = O.synthetic_train_batch(0)
+    rays = b["rays"][:37].to(DEV)
+    net = head_net(M, O.init_face_nerf(5))
+    aud, expr, lat = b["aud"].to(DEV), b["expr"].to(DEV), b["latent"].to(DEV)
+    z = M.ops.sample_coarse(rays, 7)
+    with torch.no_grad():
+        raw = net.query(rays, z, aud, expr, lat)
+        pts = rays[:, None, 0:3] + rays[:, None, 3:6] * z[..., None]
+        e10, _ = M.get_embedder(10, 0); e4, _ = M.get_embedder(4, 0)
+        x = torch.cat([e10(pts.reshape(-1, 3)), e4(rays[:, None, 8:11].expand(pts.shape).reshape(-1, 3))], -1)
+        raw2 = net(x, aud, expr, lat).reshape(37, 7, 4)
+    close(raw, raw2, 2e-5, "fused vs embedded")
+    ref = O.run_network(O.init_face_nerf(5), pts.cpu(), rays[:, 8:11].cpu(), b["aud"], b["expr"], b["latent"])
+    close(raw, ref, 5e-5, "fused vs oracle run_network")
+
+
+# ------------------------------------------------------------------------------------------------
+# the whole path
+# ------------------------------------------------------------------------------------------------
+def _preset_nets(M, g, tag, mode="fp32"):
+    c, f = O.init_face_nerf(1), O.init_face_nerf(2)
+    c["alpha_linear.weight"], c["alpha_linear.bias"] = torch.from_numpy(g[f"{tag}_alpha_w_c"]), torch.from_numpy(g[f"{tag}_alpha_b_c"])
+    f["alpha_linear.weight"], f["alpha_linear.bias"] = torch.from_numpy(g[f"{tag}_alpha_w_f"]), torch.from_numpy(g[f"{tag}_alpha_b_f"])
+    args = M.default_args(dim_aud=64, dim_expr=76, perturb=0., mlp_mode=mode)
+    net = M.Network(450, 450, 1200., O.NEAR, O.FAR, 8192, None, 64, 128, args=args)
+    net.face_nerf_coarse.load_state_dict(c); net.face_nerf_fine.load_state_dict(f)
+    return net.to(DEV)
+
+
+@pytest.mark.parametrize("tag", ["init", "dense"])
+def test_render_rays_fp32_matches_reference(M, golden, tag):
+    """All 3072 rays, 64+128 samples, against the outputs of the unmodified reference (config 1 of BASELINE.json)."""
+    g, st = golden("render_3072"), golden("render_stages")
+    net = _preset_nets(M, g, tag)
+    rays, bc = C(g["rays"]), C(g["bc_rgb"])
+    aud, expr, lat = C(g["aud"]), C(g["expr"]), C(g["latent"])
+    with torch.no_grad():
+        r = net.render_rays(rays, bc, aud, None, lat, expr, perturb=0., retraw=True)
+    tol = 1e-3                                               # north_star gate
+    for k in ("rgb_map", "acc_map", "rgb0", "acc0", "last_weight", "z_std"):
+        e = maxabs(r[k], g[f"{tag}_{k}"])
+        print(f"[{tag}] {k}: max-abs {e:.3e}")
+        assert e <= tol, f"{k}: {e:.3e}"
+        assert e <= 1e-4, f"{k}: fp32 mode should sit well inside the gate, got {e:.3e}"
+    # disp = 1/depth: compare depth-equivalent
+    close(1.0 / r["disp_map"], 1.0 / torch.from_numpy(g[f"{tag}_disp_map"]), tol, "depth (1/disp)")
+    sub = st["sub"]
+    close(r["raw"][C(sub)], st[f"{tag}_raw1"], 5e-4, "fine raw (sigma is scaled ~x100 in the dense preset)")
+
+
+def test_render_rays_perturb_pytest_draws(M, golden):
+    g, p = golden("render_3072"), golden("render_perturb")
+    net = _preset_nets(M, g, "dense")
+    idx = C(p["idx"])
+    with torch.no_grad():
+        r = net.render_rays(C(g["rays"])[idx], C(g["bc_rgb"])[idx], C(g["aud"]), None, C(g["latent"]), C(g["expr"]),
+                            perturb=1.0, pytest=True)
+    for k in ("rgb_map", "acc_map", "rgb0", "z_std", "last_weight"):
+        close(r[k], p[k], 1e-4, k)
+
+
+def test_render_dynamic_face_frame_band(M, golden):
+    """Eval-mode entry: rays generated from the pose (get_rays), chunked by batchify_rays; checked against
+    the oracle on a band of the 450x450 frame."""
+    g = golden("render_3072")
+    net = _preset_nets(M, g, "dense").eval()
+    cam = O.synthetic_camera()
+    fr = O.synthetic_frame(0)
+    H = 450
+    rows = slice(200 * 450, 200 * 450 + 900)                  # two image rows
+    with torch.no_grad():
+        out = net.render_dynamic_face(H, H, cam["focal"], fr["expr"].to(DEV), None, fr["latent"].to(DEV),
+                                      render_poses=cam["c2w"].to(DEV), chunk=65536, near=O.NEAR, far=O.FAR,
+                                      bc_rgb=fr["bc_rgb"].reshape(H, H, 3).to(DEV), aud_para=fr["aud"].to(DEV), perturb=0.)
+        rgb, disp, acc, last_w, extras = out
+        assert rgb.shape == (H, H, 3) and acc.shape == (H, H) and extras["rgb0"].shape == (H, H, 3)
+        c, f = net.face_nerf_coarse.state_dict(), net.face_nerf_fine.state_dict()
+        c = {k: v.cpu() for k, v in c.items()}; f = {k: v.cpu() for k, v in f.items()}
+        ref = O.render_rays(fr["rays"][rows], fr["bc_rgb"][rows], c, f, fr["aud"], fr["expr"], fr["latent"])
+    close(rgb.reshape(-1, 3)[rows], ref["rgb_map"], 1e-4, "frame rgb")
+    close(acc.reshape(-1)[rows], ref["acc_map"], 1e-4, "frame acc")
+    close(last_w.reshape(-1)[rows], ref["last_weight"], 1e-4, "frame last_weight")
+    # size-independent properties on the whole frame
+    assert bool(torch.isfinite(rgb).all()) and float(acc.min()) >= 0. and float(acc.max()) <= 1. + 1e-5
+
+
+def test_head_torso_composite(M, golden):
+    """Config 4: head + torso render, rgb = rgb_head * last_weight_torso + rgb_fg_torso (train_torso.py:269-270)."""
+    b = O.synthetic_train_batch(0)
+    n = 96
+    rays, bc = b["rays"][:n], b["bc_rgb"][:n]
+    args = M.default_args(dim_aud=64, dim_expr=79, perturb=0.)
+    net = M.TorsoNetwork(450, 450, 1200., O.NEAR, O.FAR, 8192, 64, 128, args=args)
+    sds = {"face_nerf_coarse": O.init_face_nerf(11, 64, 79, 32), "face_nerf_fine": O.init_face_nerf(12, 64, 79, 32),
+           "torso_coarse_nerf": O.init_face_nerf(13, 106, 0, 0), "torso_fine_nerf": O.init_face_nerf(14, 106, 0, 0)}
+    gen = torch.Generator().manual_seed(3)
+    aud, expr, lat = torch.randn(64, generator=gen), torch.randn(79, generator=gen), torch.ones(32)
+    pose = torch.eye(4); pose[:3, 3] = torch.tensor([0.02, -0.01, 0.7772])
+    for k in ("torso_coarse_nerf", "torso_fine_nerf", "face_nerf_coarse", "face_nerf_fine"):
+        sds[k] = O.normalise_density(sds[k], rays, aud if "face" in k else torch.randn(106, generator=gen),
+                                     expr if "face" in k else None, lat if "face" in k else None)
+        getattr(net, k).load_state_dict(sds[k])
+    net = net.to(DEV)
+    with torch.no_grad():
+        rgb, rgb0 = net(rays.to(DEV), rays.to(DEV), bc.to(DEV), aud.to(DEV), pose.to(DEV), expr.to(DEV), lat.to(DEV))
+        et = O.pose_to_euler_trans(pose[None])
+        sig = torch.cat([aud[:64], O.positional_encoding(et[:, :3], 3).squeeze(0), O.positional_encoding(et[:, 3:], 3).squeeze(0)])
+        h = O.render_rays(rays, bc, sds["face_nerf_coarse"], sds["face_nerf_fine"], aud, expr, lat, with_fg=True)
+        t = O.render_rays(rays, bc, sds["torso_coarse_nerf"], sds["torso_fine_nerf"], sig, None, None, with_fg=True)
+    close(rgb, O.head_torso_blend(h["rgb_map"], t["last_weight"], t["rgb_map_fg"]), 1e-4, "rgb_com")
+    close(rgb0, O.head_torso_blend(h["rgb0"], t["last_weight0"], t["rgb_map_fg0"]), 1e-4, "rgb_com0")
+
+
+def test_cpu_tensor_is_rejected(M):
+    with pytest.raises(RuntimeError):
+        M.raw2outputs(torch.zeros(2, 4, 4), torch.zeros(2, 4), torch.zeros(2, 3), torch.zeros(2, 3))

@@ -1,0 +1,114 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every symbol of include/inerf_b200.h,
+argument validation works without a GPU, and the host mirror keeps the reference's surface."""
+import ctypes
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def M():
+    import ideal_nerf_b200 as m
+    m.build()
+    return m
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "inerf_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(inerf_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(M):
+    L = M.lib()
+    syms = header_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/inerf_b200.h but not exported"
+    from ideal_nerf_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes signature table and header disagree"
+    assert L.inerf_version() == 100
+
+
+def test_argument_validation_without_gpu(M):
+    """Entry points validate shapes/pointers before touching the device: safe to call on a CPU box."""
+    L = M.lib()
+    from ideal_nerf_b200._lib import InerfNetDims
+    assert L.inerf_composite_fwd(None, None, None, 3, None, None, 4, 64, 0, None, None, None, None, None, None, None) == -1
+    assert b"NULL" in L.inerf_last_error()
+    assert L.inerf_composite_fwd(None, None, None, 3, None, None, 4, 5000, 0, None, None, None, None, None, None, None) == -2
+    assert L.inerf_composite_fwd(None, None, None, 3, None, None, 0, 64, 0, None, None, None, None, None, None, None) == 0
+    assert L.inerf_sample_pdf(None, 63, None, 62, 8, 1, 128, None, 0, 0, None, None, None, 0, None, None, None) == -2
+    bad = InerfNetDims(64, 76, 32, 128, 8, 63, 27)
+    n = ctypes.c_size_t()
+    assert L.inerf_mlp_cond_floats(ctypes.byref(bad), ctypes.byref(n)) == -4
+    ok = InerfNetDims(64, 76, 32, 256, 8, 63, 27)
+    assert L.inerf_mlp_cond_floats(ctypes.byref(ok), ctypes.byref(n)) == 0 and n.value == 8 * 256 + 3 * 128 + 4
+    assert L.inerf_mlp_fwd(7, ctypes.byref(ok), None, None, None, None, 11, None, 1, 1, None, None) == -1
+
+
+def test_no_cpu_fallback(M):
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        M.raw2outputs(torch.zeros(2, 4, 4), torch.zeros(2, 4), torch.zeros(2, 3), torch.zeros(2, 3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        M.sample_pdf(torch.zeros(2, 5), torch.zeros(2, 4), 8, det=True)
+    net = M.FaceNeRF(dim_aud=64, dim_latent=32, dim_expr=76)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.zeros(4, 90), torch.zeros(64), torch.zeros(76), torch.zeros(32))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "ideal-nerf_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle", src, flags=re.M), f"{f} imports oracle/"
+                assert "render_oracle" not in src or f == "sample_pdf.cu", f
+
+
+def test_reference_surface(M):
+    """Names and signatures of the reference's Python surface."""
+    sig = inspect.signature
+    assert list(sig(M.raw2outputs).parameters) == ["raw", "z_vals", "rays_d", "bc_rgb", "raw_noise_std", "white_bkgd", "pytest"]
+    assert list(sig(M.sample_pdf).parameters)[:5] == ["bins", "weights", "N_samples", "det", "pytest"]
+    assert list(sig(M.get_embedder).parameters) == ["multires", "i", "input_dims"]
+    assert list(sig(M.get_rays).parameters) == ["H", "W", "focal", "c2w", "cx", "cy"]
+    assert list(sig(M.FaceNeRF.forward).parameters) == ["self", "x", "aud", "expr", "latent_code"]
+    assert list(sig(M.FaceNeRF.__init__).parameters)[1:11] == ["D", "W", "input_ch", "input_ch_views", "dim_aud", "dim_latent",
+                                                             "dim_expr", "output_ch", "skips", "use_viewdirs"]
+    rr = list(sig(M.Network.render_rays).parameters)
+    assert rr[:7] == ["self", "rays", "bc_rgb", "aud_para", "poses", "latent_code", "expr"]
+    assert rr[7:] == ["retraw", "lindisp", "perturb", "white_bkgd", "raw_noise_std", "attention_embed_ln", "pytest"]
+    fr = list(sig(M.render_rays).parameters)
+    assert fr[:15] == ["ray_batch", "bc_rgb", "aud_para", "network_fn", "network_query_fn", "N_samples", "retraw", "lindisp",
+                       "perturb", "N_importance", "network_fine", "white_bkgd", "raw_noise_std", "verbose", "pytest"]
+    net = M.Network(450, 450, 1200., 0.57, 1.17, 8192, None, 64, 128)
+    keys = set(net.state_dict())
+    for pre in ("face_nerf_coarse.", "face_nerf_fine."):
+        for l in [f"pts_linears.{i}" for i in range(8)] + [f"views_linears.{i}" for i in range(3)] + \
+                ["feature_linear", "alpha_linear", "rgb_linear"]:
+            assert pre + l + ".weight" in keys and pre + l + ".bias" in keys
+    assert net.face_nerf_coarse.pts_linears[0].weight.shape == (256, 63 + 64 + 76 + 32)
+    assert net.face_nerf_coarse.pts_linears[5].weight.shape == (256, 256 + 235)
+    assert net.face_nerf_coarse.views_linears[0].weight.shape == (128, 27 + 256 + 76)
+
+
+def test_config_flags(M, tmp_path):
+    p = M.config_parser()
+    a = p.parse_args([])
+    assert (a.N_samples, a.N_importance, a.chunk, a.netchunk, a.perturb) == (64, 128, 8192, 65536, 1.0)
+    assert a.use_viewdirs is True and a.white_bkgd is True                 # store_false flags default to True
+    a = p.parse_args(["--N_sample", "32", "--dim_aud", "64", "--dim_expr", "76", "--near", "0.5772", "--far", "1.1772"])
+    assert a.N_samples == 32 and a.dim_aud == 64 and a.dim_expr == 76    # README's N_sample spelling still works
+    cfg = tmp_path / "paper_model.txt"
+    cfg.write_text("expname=torso_bg\nN_sample=64\nN_importance=128\nlrate=3e-4\nN_rand=3072\nmouth_rays=512\ndim_expr=79\ndim_aud=64\n"
+                   "near=0.5674083709716797\nfar=1.1674083709716796\n")
+    a = p.parse_args(["--config", str(cfg), "--N_rand", "1024"])
+    assert a.N_samples == 64 and a.lrate == 3e-4 and a.mouth_rays == 512 and a.dim_expr == 79
+    assert a.N_rand == 1024 and abs(a.near - 0.5674083709716797) < 1e-15
