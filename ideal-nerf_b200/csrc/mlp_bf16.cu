@@ -1,7 +1,527 @@
-// placeholder until the tcgen05 kernel lands
+// FaceNeRF MLP, bf16 mode: the fused tensor-core kernel (tcgen05.mma, accumulators in TMEM, weights
+// streamed by the TMA engine, activations resident in shared memory from the positional encoding
+// to the (r,g,b,sigma) output).
+//
+// Reference: models/face_nerf.py:40-80, NeRFs/HeadNeRF/train/audio_exp_nerf.py:332,376-394,
+// NeRFs/HeadNeRF/helper.py:174-204.  Folded per-point network:
+//   L0 63->256, L1-4 256->256, L5 (63+256)->256, L6-7 256->256, alpha 256->1,
+//   V0 (256 [+27 view cols])->128, V1-2 128->128, rgb 128->3.
+//
+// Work decomposition (one persistent CTA per SM, 512 threads):
+//   * a CTA iteration owns 256 consecutive points = two 128-row "slots" that advance in lock step,
+//     so every streamed weight byte feeds 256 rows (halves the L2->SM weight traffic of a 128-row tile);
+//   * every layer is issued as two output halves h0,h1 (N/2 columns each, M=128, K=16 per
+//     tcgen05.mma).  The epilogue of half h0 (TMEM -> +bias -> ReLU -> bf16 -> swizzled smem) runs
+//     while the tensor pipe computes h1, and the epilogue of h1 overlaps the first K-blocks of the
+//     next layer, so the pipe never waits for an epilogue.  Activations are updated IN PLACE:
+//     h1 reads the K-blocks that epi(h0) will overwrite first and commits (C1) before they are
+//     written; commit C0 = "h0 accumulators complete", C2 = "layer complete";
+//   * roles: warp 0 = weight producer (cp.async.bulk, 16 KB stages, mbarrier ring), warp 1 = MMA
+//     issuer (one thread), warp 2 = TMEM allocator, warps 4-11 = epilogue (one row per thread, 4 warps
+//     per slot), warps 12-15 = positional-encoding producers for the NEXT iteration (2 rows/thread);
+//   * gamma(viewdir) is constant per ray, so its 27 columns of views_linears.0 become a per-ray fp32
+//     bias vector (computed by the PE warps) added in the V0 epilogue instead of a K=32 MMA block;
+//   * alpha_linear (256->1) and rgb_linear (128->3) are fp32 dot products inside the L7 / V2 epilogues.
+// Weights are pre-packed (inerf_mlp_pack) as the exact shared-memory image of every stage: bf16,
+// K-major, 128-byte swizzle, in MMA issue order, so a stage is ONE contiguous bulk copy.
+#include <cuda_bf16.h>
+
 #include "mlp_common.cuh"
-namespace inerf {
-int mlp_bf16_launch(const MlpArgs&, bool, cudaStream_t) { return fail(INERF_E_UNSUPPORTED, "bf16 MLP mode not built yet"); }
-int mlp_bf16_packed_bytes(const InerfNetDims*, size_t* bytes) { *bytes = 0; return fail(INERF_E_UNSUPPORTED, "bf16 MLP mode not built yet"); }
-int mlp_bf16_pack(const InerfNetDims*, const float* const*, void*, cudaStream_t) { return fail(INERF_E_UNSUPPORTED, "bf16 MLP mode not built yet"); }
+#include "sm100_ptx.cuh"
+
+using namespace inerf;
+using namespace sm100;
+
+namespace {
+
+constexpr int NSTAGE = 3;
+constexpr int STAGE_BYTES = 16384;
+constexpr int MAX_STEPS = 80;
+constexpr int RMAX = 5;            // rays a 128-row slot can touch (s >= 32)
+constexpr int NTHREADS_BF16 = 512;
+constexpr int N_EPI = 256, N_PE = 128;
+
+// event bits
+enum { W_E0 = 1, W_E1 = 2, W_PE = 4 };
+enum { C_C0 = 1, C_C1 = 2, C_C2 = 4, C_PEFREE = 8 };
+
+struct Step {
+    uint8_t a_kb;      // 0..3 activation K-block, 4 = positional-encoding block
+    uint8_t n8;        // MMA N / 8
+    uint8_t acc_col;   // accumulator column offset inside the slot (0, 64, 128)
+    uint8_t first;     // first MMA of its (layer, half): overwrite instead of accumulate
+    uint8_t wait;      // W_* bits
+    uint8_t commit;    // C_* bits
+    uint8_t layer;     // 0..10
+    uint8_t pad;
+    uint32_t offset;   // byte offset of this stage's image inside the packed blob
+};
+
+struct PackStep {
+    int w_index, ldw, n0, rows, wcol;   // weight rows [n0, n0+rows), columns wcol .. wcol+63 (kmax valid)
+    int kmax;
+    uint32_t offset;
+};
+
+struct Schedule {
+    int n_steps;
+    Step steps[MAX_STEPS];
+    PackStep pack[MAX_STEPS];
+    uint32_t total_bytes;
+};
+
+__constant__ Step c_steps[MAX_STEPS];
+
+// smem map (bytes from the 1024-aligned base)
+constexpr int OFF_ACT = 0;                               // [2][4][16384]
+constexpr int OFF_PE = 131072;                           // [2][16384]
+constexpr int OFF_W = 163840;                            // [NSTAGE][16384]
+constexpr int OFF_BIAS = OFF_W + NSTAGE * STAGE_BYTES;   // 2436 floats (CondLayout)
+constexpr int OFF_AW = OFF_BIAS + 9744;                  // alpha_linear.weight 256 floats
+constexpr int OFF_RW = OFF_AW + 1024;                    // rgb_linear.weight 3x128 floats
+constexpr int OFF_DIRB = OFF_RW + 1536;                  // [2][RMAX][128] floats
+constexpr int OFF_BAR = OFF_DIRB + 2 * RMAX * 128 * 4;   // mbarriers
+constexpr int SMEM_BYTES = OFF_BAR + 256;
+constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;            // slack for the 1024-byte alignment
+static_assert(SMEM_ALLOC <= 232448, "shared memory budget");
+
+struct Bars {
+    uint64_t wfull[NSTAGE], wempty[NSTAGE];
+    uint64_t cbar[3];        // C0, C1, C2   (tcgen05.commit, once per layer)
+    uint64_t ebar[2];        // E0, E1       (256 epilogue threads, once per layer)
+    uint64_t pe_ready;       // 128 PE threads, once per iteration
+    uint64_t pe_free;        // commit after the last MMA that reads the PE block
+    uint64_t dirb_ready;     // 128 PE threads
+    uint64_t dirb_free;      // 256 epilogue threads
+    uint32_t tmem_base;
+};
+
+struct LayerInfo { int N, bias_off; };
+
+__device__ __forceinline__ LayerInfo layer_info(int l) {
+    LayerInfo r;
+    if (l < 8) { r.N = 256; r.bias_off = l * 256; }
+    else { r.N = 128; r.bias_off = 8 * 256 + (l - 8) * 128; }
+    return r;
 }
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <bool TRACE>
+__global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, int n_steps, int n_rays, float* __restrict__ trace) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    Bars* bars = reinterpret_cast<Bars*>(sm + OFF_BAR);
+    float* s_bias = reinterpret_cast<float*>(sm + OFF_BIAS);
+    float* s_aw = reinterpret_cast<float*>(sm + OFF_AW);
+    float* s_rw = reinterpret_cast<float*>(sm + OFF_RW);
+    float* s_dirb = reinterpret_cast<float*>(sm + OFF_DIRB);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long n_iter = (a.P + 255) / 256;
+
+    // ---- one-time setup -------------------------------------------------------------------
+    for (int i = tid; i < 2436; i += NTHREADS_BF16) s_bias[i] = a.cond[i];
+    for (int i = tid; i < 256; i += NTHREADS_BF16) s_aw[i] = a.w[P_ALPHA_W][i];
+    for (int i = tid; i < 384; i += NTHREADS_BF16) s_rw[i] = a.w[P_RGB_W][i];
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars->wfull[s], 1); mbar_init(&bars->wempty[s], 1); }
+        for (int j = 0; j < 3; ++j) mbar_init(&bars->cbar[j], 1);
+        for (int j = 0; j < 2; ++j) mbar_init(&bars->ebar[j], N_EPI);
+        mbar_init(&bars->pe_ready, N_PE);
+        mbar_init(&bars->pe_free, 1);
+        mbar_init(&bars->dirb_ready, N_PE);
+        mbar_init(&bars->dirb_free, N_EPI);
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(&bars->tmem_base, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        // ================= weight producer ==================================================
+        if (lane == 0) {
+            const uint8_t* blob = reinterpret_cast<const uint8_t*>(a.packed);
+            uint32_t g = 0;
+            for (long long it = blockIdx.x; it < n_iter; it += gridDim.x) {
+                for (int s = 0; s < n_steps; ++s, ++g) {
+                    const uint32_t stage = g % NSTAGE, round = g / NSTAGE;
+                    mbar_wait(&bars->wempty[stage], (round & 1) ^ 1);
+                    const uint32_t bytes = (uint32_t)c_steps[s].n8 * 8u * 128u;
+                    mbar_arrive_expect_tx(&bars->wfull[stage], bytes);
+                    bulk_g2s(sm + OFF_W + stage * STAGE_BYTES, blob + c_steps[s].offset, bytes, &bars->wfull[stage]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer ========================================================
+        if (lane == 0) {
+            uint32_t g = 0, layer_ctr = 0, iter_ctr = 0;
+            const uint32_t act_base = smem_u32(sm + OFF_ACT), pe_base = smem_u32(sm + OFF_PE), w_base = smem_u32(sm + OFF_W);
+            for (long long it = blockIdx.x; it < n_iter; it += gridDim.x, ++iter_ctr) {
+                int cur_layer = 0;
+                for (int s = 0; s < n_steps; ++s, ++g) {
+                    const Step st = c_steps[s];
+                    if (st.layer != cur_layer) { cur_layer = st.layer; ++layer_ctr; }
+                    // events produced by the epilogue of the previous layer (global layer counter - 1)
+                    if (st.wait & (W_E0 | W_E1)) {
+                        if (layer_ctr > 0) {
+                            const uint32_t par = (layer_ctr - 1) & 1;
+                            if (st.wait & W_E0) mbar_wait(&bars->ebar[0], par);
+                            if (st.wait & W_E1) mbar_wait(&bars->ebar[1], par);
+                        }
+                    }
+                    if (st.wait & W_PE) mbar_wait(&bars->pe_ready, iter_ctr & 1);
+                    const uint32_t stage = g % NSTAGE, round = g / NSTAGE;
+                    mbar_wait(&bars->wfull[stage], round & 1);
+                    tc_fence_after();
+                    const uint32_t idesc = umma_idesc_bf16(128, st.n8 * 8);
+                    const uint64_t bd = umma_desc_sw128(w_base + stage * STAGE_BYTES);
+#pragma unroll
+                    for (int slot = 0; slot < 2; ++slot) {
+                        const uint32_t a_addr = (st.a_kb < 4) ? act_base + slot * 65536 + st.a_kb * 16384 : pe_base + slot * 16384;
+                        const uint64_t ad = umma_desc_sw128(a_addr);
+                        const uint32_t d = tmem_base + slot * 256 + st.acc_col;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (st.first && k == 0) ? 0u : 1u);
+                    }
+                    umma_commit(&bars->wempty[stage]);
+                    if (st.commit & C_C0) umma_commit(&bars->cbar[0]);
+                    if (st.commit & C_C1) umma_commit(&bars->cbar[1]);
+                    if (st.commit & C_C2) umma_commit(&bars->cbar[2]);
+                    if (st.commit & C_PEFREE) umma_commit(&bars->pe_free);
+                }
+                ++layer_ctr;      // the next iteration's L0 is a new layer
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ================= epilogue: one row per thread ======================================
+        const int slot = (warp - 4) >> 2;
+        const int row = ((warp & 3) << 5) + lane;
+        const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) << 5) << 16) + slot * 256;
+        uint8_t* act = sm + OFF_ACT + slot * 65536;
+        const uint32_t row_off = (row >> 3) * 1024 + (row & 7) * 128;
+        const uint32_t rsw = row & 7;
+        uint32_t layer_ctr = 0, iter_ctr = 0;
+        for (long long it = blockIdx.x; it < n_iter; it += gridDim.x, ++iter_ctr) {
+            const long long p0 = it * 256 + slot * 128;
+            long long p = p0 + row;
+            const bool in_range = p < a.P;
+            if (!in_range) p = a.P - 1;
+            const int ray_local = (int)(p / a.s - min(p0, a.P - 1) / a.s);
+            float alpha = 0.f, rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+            for (int l = 0; l < 11; ++l, ++layer_ctr) {
+                const LayerInfo li = layer_info(l);
+                const int NH = li.N >> 1;
+                const uint32_t par = layer_ctr & 1;
+                if (l == 8) mbar_wait(&bars->dirb_ready, iter_ctr & 1);
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    mbar_wait(&bars->cbar[h == 0 ? 0 : 2], par);
+                    tc_fence_after();
+                    uint32_t packed[64];
+                    const int nchunk = NH >> 5;      // 4 (N=256) or 2 (N=128)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (c < nchunk) {
+                            uint32_t r[32];
+                            tmem_ld32(t_lane + h * NH + c * 32, r);
+                            tmem_wait_ld();
+                            const int f0 = h * NH + c * 32;                 // first output feature of the chunk
+                            const float* bsrc = s_bias + li.bias_off + f0;
+                            const float* dsrc = s_dirb + (slot * RMAX + ray_local) * 128 + f0;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                float v0 = __uint_as_float(r[j]) + bsrc[j];
+                                float v1 = __uint_as_float(r[j + 1]) + bsrc[j + 1];
+                                if (l == 8) { v0 += dsrc[j]; v1 += dsrc[j + 1]; }
+                                if (l == 7) { alpha = fmaf(fmaxf(v0, 0.f), s_aw[f0 + j], alpha); alpha = fmaf(fmaxf(v1, 0.f), s_aw[f0 + j + 1], alpha); }
+                                if (l == 10) {
+                                    const float r0 = fmaxf(v0, 0.f), r1 = fmaxf(v1, 0.f);
+                                    rgb0 = fmaf(r0, s_rw[f0 + j], rgb0); rgb0 = fmaf(r1, s_rw[f0 + j + 1], rgb0);
+                                    rgb1 = fmaf(r0, s_rw[128 + f0 + j], rgb1); rgb1 = fmaf(r1, s_rw[128 + f0 + j + 1], rgb1);
+                                    rgb2 = fmaf(r0, s_rw[256 + f0 + j], rgb2); rgb2 = fmaf(r1, s_rw[256 + f0 + j + 1], rgb2);
+                                }
+                                packed[c * 16 + (j >> 1)] = pack_bf16x2_relu(v0, v1);
+                                if constexpr (TRACE) {      // post-activation values of the first 256 points, [11][256][256]
+                                    if (it == 0) {
+                                        float* tr = trace + ((size_t)l * 256 + slot * 128 + row) * 256 + f0 + j;
+                                        tr[0] = fmaxf(v0, 0.f); tr[1] = fmaxf(v1, 0.f);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    if (l != 10) {
+                        if (h == 0) mbar_wait(&bars->cbar[1], par);      // h1 has finished reading the K-blocks written below
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            if (c < nchunk) {
+                                const int f0 = h * NH + c * 32;
+                                uint8_t* kb = act + (f0 >> 6) * 16384 + row_off;
+                                const int ch0 = (f0 & 63) >> 3;                // first 16-byte chunk inside the 128-byte row
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    uint4 v = make_uint4(packed[c * 16 + q * 4], packed[c * 16 + q * 4 + 1],
+                                                         packed[c * 16 + q * 4 + 2], packed[c * 16 + q * 4 + 3]);
+                                    *reinterpret_cast<uint4*>(kb + (((ch0 + q) ^ rsw) << 4)) = v;
+                                }
+                            }
+                        }
+                        fence_proxy_async_smem();
+                    }
+                    mbar_arrive(&bars->ebar[h]);
+                }
+                if (l == 8) mbar_arrive(&bars->dirb_free);
+            }
+            if (in_range) {
+                float4 o;
+                o.x = rgb0 + s_bias[8 * 256 + 3 * 128 + 1];
+                o.y = rgb1 + s_bias[8 * 256 + 3 * 128 + 2];
+                o.z = rgb2 + s_bias[8 * 256 + 3 * 128 + 3];
+                o.w = alpha + s_bias[8 * 256 + 3 * 128];
+                reinterpret_cast<float4*>(a.out)[p] = o;
+            }
+        }
+    } else if (warp >= 12) {
+        // ================= positional encoding + per-ray view bias producers ==================
+        const int t = tid - 12 * 32;                 // 0..127: row of both slots, and output feature of the view bias
+        float wdir[27];                              // views_linears.0.weight[t, 256:283], resident in registers
+        {
+            const float* wrow = a.w[P_VIEWS_W] + (size_t)t * (283 + a.dim_expr) + 256;
+#pragma unroll
+            for (int j = 0; j < 27; ++j) wdir[j] = wrow[j];
+        }
+        uint32_t iter_ctr = 0;
+        for (long long it = blockIdx.x; it < n_iter; it += gridDim.x, ++iter_ctr) {
+            // ---- gamma_10(o + d z) for row t of both slots ---------------------------------------
+            uint32_t pk[2][32];
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+                long long p = it * 256 + sl * 128 + t;
+                if (p > a.P - 1) p = a.P - 1;
+                const long long ray = p / a.s;
+                const float* r = a.rays + ray * a.ray_stride;
+                const float zz = a.z[p];
+                float v[64];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[c] = __fadd_rn(r[c], __fmul_rn(r[3 + c], zz));
+#pragma unroll
+                for (int f = 0; f < 10; ++f)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        float sn, cs;
+                        sincosf(v[c] * (float)(1 << f), &sn, &cs);
+                        v[3 + 6 * f + c] = sn;
+                        v[6 + 6 * f + c] = cs;
+                    }
+                v[63] = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) pk[sl][j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            }
+            if (iter_ctr > 0) mbar_wait(&bars->pe_free, (iter_ctr - 1) & 1);
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+                uint8_t* dst = sm + OFF_PE + sl * 16384 + (t >> 3) * 1024 + (t & 7) * 128;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<uint4*>(dst + ((q ^ (t & 7)) << 4)) =
+                        make_uint4(pk[sl][4 * q], pk[sl][4 * q + 1], pk[sl][4 * q + 2], pk[sl][4 * q + 3]);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&bars->pe_ready);
+            // ---- per-ray view bias: lane q < 2*RMAX encodes ray q, the warp shares it by shuffle ----
+            {
+                float enc[27];
+                const int q = lane;
+                if (q < 2 * RMAX) {
+                    const int sl = q / RMAX, rl = q - sl * RMAX;
+                    long long pfirst = it * 256 + sl * 128;
+                    if (pfirst > a.P - 1) pfirst = a.P - 1;
+                    long long ray = pfirst / a.s + rl;
+                    if (ray > n_rays - 1) ray = n_rays - 1;
+                    const float* r = a.rays + ray * a.ray_stride + (a.ray_stride - 3);
+                    enc[0] = r[0]; enc[1] = r[1]; enc[2] = r[2];
+#pragma unroll
+                    for (int f = 0; f < 4; ++f)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            float sn, cs;
+                            sincosf(enc[c] * (float)(1 << f), &sn, &cs);
+                            enc[3 + 6 * f + c] = sn;
+                            enc[6 + 6 * f + c] = cs;
+                        }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 27; ++j) enc[j] = 0.f;
+                }
+                if (iter_ctr > 0) mbar_wait(&bars->dirb_free, (iter_ctr - 1) & 1);
+                for (int q2 = 0; q2 < 2 * RMAX; ++q2) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 27; ++j) acc = fmaf(wdir[j], __shfl_sync(0xffffffffu, enc[j], q2), acc);
+                    s_dirb[q2 * 128 + t] = acc;
+                }
+                mbar_arrive(&bars->dirb_ready);
+            }
+        }
+    }
+
+    // ---- teardown ---------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// schedule (host)
+// ---------------------------------------------------------------------------------------------
+struct LayerDesc { int N, n_act_kb; bool has_pe; int w_index; int ldw, wcol_act; };
+
+Schedule build_schedule(const InerfNetDims* d) {
+    const int C = d->dim_aud + d->dim_expr + d->dim_latent, E = d->dim_expr;
+    LayerDesc L[11];
+    L[0] = {256, 0, true, 0, 63 + C, 0};
+    for (int l = 1; l < 8; ++l) L[l] = {256, 4, false, 2 * l, 256, 0};
+    L[5] = {256, 4, true, 10, 319 + C, 63 + C};
+    L[8] = {128, 4, false, P_VIEWS_W, 283 + E, 0};
+    L[9] = {128, 2, false, P_VIEWS_W + 2, 128, 0};
+    L[10] = {128, 2, false, P_VIEWS_W + 4, 128, 0};
+    Schedule S{};
+    uint32_t off = 0;
+    int n = 0;
+    for (int l = 0; l < 11; ++l) {
+        const int NH = L[l].N / 2;
+        const int prevN = l == 0 ? 128 : L[l - 1].N;          // L0 follows V2 of the previous iteration
+        const int n_out_h0 = NH / 64;                         // K-blocks epi(h0) overwrites: kb < n_out_h0
+        for (int h = 0; h < 2; ++h) {
+            int order[5], cnt = 0;                            // K-block order of this half (4 = PE)
+            if (h == 0) {
+                for (int kb = 0; kb < L[l].n_act_kb; ++kb) order[cnt++] = kb;
+                if (L[l].has_pe) order[cnt++] = 4;
+            } else {
+                for (int kb = 0; kb < L[l].n_act_kb; ++kb) if (kb < n_out_h0) order[cnt++] = kb;
+                for (int kb = 0; kb < L[l].n_act_kb; ++kb) if (kb >= n_out_h0) order[cnt++] = kb;
+                if (L[l].has_pe) order[cnt++] = 4;
+            }
+            int n_first = 0;                                  // how many leading K-blocks of h1 are "overwritten by h0" ones
+            if (h == 1) for (int i = 0; i < cnt; ++i) if (order[i] < 4 && order[i] < n_out_h0) ++n_first;
+            for (int i = 0; i < cnt; ++i) {
+                Step& st = S.steps[n];
+                PackStep& pk = S.pack[n];
+                st.a_kb = (uint8_t)order[i];
+                st.n8 = (uint8_t)(NH / 8);
+                st.acc_col = (uint8_t)(h * NH);
+                st.first = (i == 0);
+                st.layer = (uint8_t)l;
+                st.wait = 0;
+                if (order[i] < 4) {
+                    // which half of the previous layer's epilogue produced this K-block
+                    const int kb_per_half = prevN / 128;      // 2 for N=256, 1 for N=128
+                    st.wait = (order[i] < kb_per_half) ? W_E0 : W_E1;
+                } else if (l == 0) {
+                    st.wait = W_PE | W_E0 | W_E1;             // new iteration: PE ready and both accumulator halves drained
+                }
+                st.commit = 0;
+                const bool last = (i == cnt - 1);
+                if (h == 0 && last) st.commit |= C_C0;
+                if (h == 1) {
+                    if (n_first > 0 ? (i == n_first - 1) : last) st.commit |= C_C1;
+                    if (last) st.commit |= C_C2;
+                    if (last && l == 5) st.commit |= C_PEFREE;
+                }
+                st.offset = off;
+                pk.w_index = L[l].w_index; pk.ldw = L[l].ldw; pk.n0 = h * NH; pk.rows = NH; pk.offset = off;
+                if (order[i] == 4) { pk.wcol = 0; pk.kmax = 63; }
+                else { pk.wcol = L[l].wcol_act + order[i] * 64; pk.kmax = 64; }
+                off += (uint32_t)NH * 128u;
+                ++n;
+            }
+        }
+    }
+    S.n_steps = n;
+    S.total_bytes = off;
+    return S;
+}
+
+struct PackArgs {
+    const float* w[INERF_N_PARAMS];
+    PackStep st[MAX_STEPS];
+    uint8_t* blob;
+};
+
+__global__ void pack_kernel(const PackArgs* __restrict__ pa_ptr) {
+    const PackArgs& pa = *pa_ptr;
+    const PackStep st = pa.st[blockIdx.x];
+    const float* W = pa.w[st.w_index];
+    for (int i = threadIdx.x; i < st.rows * 64; i += blockDim.x) {
+        const int r = i >> 6, c = i & 63;
+        const float v = (c < st.kmax) ? W[(size_t)(st.n0 + r) * st.ldw + st.wcol + c] : 0.f;
+        *reinterpret_cast<__nv_bfloat16*>(pa.blob + st.offset + sw128_offset(r, c)) = __float2bfloat16_rn(v);
+    }
+}
+
+}  // namespace
+
+namespace inerf {
+
+int mlp_bf16_packed_bytes(const InerfNetDims* d, size_t* bytes) {
+    Schedule S = build_schedule(d);
+    *bytes = (size_t)S.total_bytes + sizeof(PackArgs);        // tail: scratch for the pack kernel's argument table
+    return INERF_OK;
+}
+
+int mlp_bf16_pack(const InerfNetDims* d, const float* const* params_host, void* packed, cudaStream_t st) {
+    if ((uintptr_t)packed & 15) return fail(INERF_E_ALIGN, "inerf_mlp_pack: packed must be 16-byte aligned");
+    Schedule S = build_schedule(d);
+    PackArgs pa{};
+    for (int i = 0; i < INERF_N_PARAMS; ++i) pa.w[i] = params_host[i];
+    for (int i = 0; i < S.n_steps; ++i) pa.st[i] = S.pack[i];
+    pa.blob = reinterpret_cast<uint8_t*>(packed);
+    PackArgs* dev_args = reinterpret_cast<PackArgs*>(pa.blob + S.total_bytes);
+    cudaError_t e = cudaMemcpyAsync(dev_args, &pa, sizeof(pa), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { set_error("inerf_mlp_pack: %s", cudaGetErrorString(e)); return (int)e; }
+    // pa lives on the stack: the copy above is from pageable memory and is staged before return
+    pack_kernel<<<S.n_steps, 256, 0, st>>>(dev_args);
+    return check_launch("inerf_mlp_pack");
+}
+
+int mlp_bf16_launch(const MlpArgs& a, bool embedded, cudaStream_t st) {
+    if (embedded)
+        return fail(INERF_E_UNSUPPORTED, "bf16 mode is built for the fused (rays, z) entry; FaceNeRF.forward on embedded rows runs in fp32 mode");
+    if (a.s < 32) return fail(INERF_E_UNSUPPORTED, "bf16 mode needs at least 32 samples per ray (a 128-row slot may touch at most 5 rays)");
+    if ((uintptr_t)a.packed & 15) return fail(INERF_E_ALIGN, "inerf_mlp_fwd: packed weights must be 16-byte aligned");
+    static thread_local int configured_dev = -1;
+    static Schedule S;
+    static bool have_schedule = false;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!have_schedule) {
+        InerfNetDims d{64, 76, 32, 256, 8, 63, 27};          // the step table does not depend on the conditioning dims
+        S = build_schedule(&d);
+        have_schedule = true;
+    }
+    if (configured_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+        if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_steps, S.steps, sizeof(Step) * MAX_STEPS);
+        if (e != cudaSuccess) { set_error("mlp_bf16: setup: %s", cudaGetErrorString(e)); return (int)e; }
+        configured_dev = dev;
+    }
+    const long long n_iter = (a.P + 255) / 256;
+    const int grid = (int)(n_iter < (long long)num_sms() ? n_iter : (long long)num_sms());
+    const int n_rays = (int)(a.P / a.s);
+    if (a.trace) mlp_bf16_kernel<true><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, a.trace);
+    else mlp_bf16_kernel<false><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, nullptr);
+    return check_launch("inerf_mlp_fwd[bf16]");
+}
+
+}  // namespace inerf

@@ -18,6 +18,7 @@ struct MlpArgs {
     float* out;                       // (P,4)
     int cond_dim;                     // dim_aud + dim_expr + dim_latent
     int dim_expr;
+    float* trace;                     // optional (bf16 path): post-activation values of the first 256 points, [11][256][256]
 };
 
 int mlp_fp32_launch(const MlpArgs& a, bool embedded, cudaStream_t st);

@@ -311,6 +311,19 @@ def mlp_fwd(mode, dims, params, packed, cond, rays, z):
     return raw
 
 
+def mlp_fwd_trace(mode, dims, params, packed, cond, rays, z):
+    """bf16 kernel with the per-layer activation trace of the first 256 points: returns (raw, trace[11,256,256])."""
+    rays, z = f32c(rays, "rays"), f32c(z, "z_vals")
+    n, s = z.shape
+    raw = torch.empty((n, s, 4), device=z.device)
+    trace = torch.zeros((11, 256, 256), device=z.device)
+    arr = param_array(params)
+    with torch.cuda.device(z.device):
+        call("inerf_mlp_fwd_trace", _lib.lib().inerf_mlp_fwd_trace, mode, ctypes.byref(dims), arr, ptr(packed), ptr(cond),
+             ptr(rays), rays.shape[1], ptr(z), n, s, ptr(raw), ptr(trace), stream())
+    return raw, trace
+
+
 def mlp_fwd_embedded(mode, dims, params, packed, cond, x):
     x = f32c(x, "x")
     assert x.dim() == 2 and x.shape[1] == 90, "x must be (P, 63+27)"

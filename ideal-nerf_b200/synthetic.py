@@ -2,8 +2,8 @@
 audio / expression / latent codes, random-init FaceNeRF weights with the normalised-density preset.
 
 Used by bench.py and __graft_entry__.smoke(); there is no dataset or checkpoint in this environment.
-The tensors follow the same generator sequence as oracle/render_oracle.py::synthetic_frame so both
-arms of the benchmark see the same data, but nothing here imports the oracle.
+The tensors follow the same generator sequence as the test oracle's synthetic_frame so both arms of
+the benchmark see the same data, but nothing here imports the test infrastructure.
 """
 import torch
 

@@ -177,6 +177,14 @@ int inerf_mlp_fwd(int mode, const InerfNetDims* dims, const float* const* params
                   const float* cond, const float* rays, int ray_stride, const float* z, int n, int s,
                   float* raw, void* stream);
 
+/* Diagnostic twin of inerf_mlp_fwd for the bf16 kernel: additionally writes the post-ReLU activations of
+ * every layer (L0..L7, V0..V2; fp32, before the bf16 rounding) of the FIRST 256 points to
+ * trace [11][256][256] (columns >= 128 of V0..V2 are not written).  Used by the parity tests to localise
+ * a mismatch to a layer. */
+int inerf_mlp_fwd_trace(int mode, const InerfNetDims* dims, const float* const* params_host, const void* packed,
+                        const float* cond, const float* rays, int ray_stride, const float* z, int n, int s,
+                        float* raw, float* trace, void* stream);
+
 /* FaceNeRF.forward on already-embedded inputs x (p, in_xyz+in_views) -- the reference module's own
  * call signature (face_nerf.py:40).  out (p, 4). */
 int inerf_mlp_fwd_embedded(int mode, const InerfNetDims* dims, const float* const* params_host,
