@@ -105,6 +105,43 @@ __device__ __forceinline__ LayerInfo layer_info(int l) {
     return r;
 }
 
+// One 32-column chunk of an epilogue: +bias (+per-ray view bias), ReLU, bf16 pack; KIND 1 also accumulates
+// alpha_linear, KIND 3 rgb_linear, in fp32 from the un-rounded activations.
+template <int KIND, bool TRACE>
+__device__ __forceinline__ void epi_convert(const uint32_t (&r)[32], uint32_t* __restrict__ packed16, const float* __restrict__ bsrc,
+                                            const float* __restrict__ dsrc, const float* __restrict__ aw, const float* __restrict__ rw,
+                                            float& alpha, float& rgb0, float& rgb1, float& rgb2, float* tr, bool dump) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(bsrc + j);
+        float v[4] = {__uint_as_float(r[j]) + b.x, __uint_as_float(r[j + 1]) + b.y, __uint_as_float(r[j + 2]) + b.z,
+                      __uint_as_float(r[j + 3]) + b.w};
+        if constexpr (KIND == 2) {
+            const float4 d = *reinterpret_cast<const float4*>(dsrc + j);
+            v[0] += d.x; v[1] += d.y; v[2] += d.z; v[3] += d.w;
+        }
+        if constexpr (KIND == 1) {
+            const float4 w = *reinterpret_cast<const float4*>(aw + j);
+            alpha = fmaf(fmaxf(v[0], 0.f), w.x, alpha); alpha = fmaf(fmaxf(v[1], 0.f), w.y, alpha);
+            alpha = fmaf(fmaxf(v[2], 0.f), w.z, alpha); alpha = fmaf(fmaxf(v[3], 0.f), w.w, alpha);
+        }
+        if constexpr (KIND == 3) {
+            const float q[4] = {fmaxf(v[0], 0.f), fmaxf(v[1], 0.f), fmaxf(v[2], 0.f), fmaxf(v[3], 0.f)};
+            const float4 w0 = *reinterpret_cast<const float4*>(rw + j);
+            const float4 w1 = *reinterpret_cast<const float4*>(rw + 128 + j);
+            const float4 w2 = *reinterpret_cast<const float4*>(rw + 256 + j);
+            rgb0 = fmaf(q[0], w0.x, rgb0); rgb0 = fmaf(q[1], w0.y, rgb0); rgb0 = fmaf(q[2], w0.z, rgb0); rgb0 = fmaf(q[3], w0.w, rgb0);
+            rgb1 = fmaf(q[0], w1.x, rgb1); rgb1 = fmaf(q[1], w1.y, rgb1); rgb1 = fmaf(q[2], w1.z, rgb1); rgb1 = fmaf(q[3], w1.w, rgb1);
+            rgb2 = fmaf(q[0], w2.x, rgb2); rgb2 = fmaf(q[1], w2.y, rgb2); rgb2 = fmaf(q[2], w2.z, rgb2); rgb2 = fmaf(q[3], w2.w, rgb2);
+        }
+        packed16[(j >> 1)] = pack_bf16x2_relu(v[0], v[1]);
+        packed16[(j >> 1) + 1] = pack_bf16x2_relu(v[2], v[3]);
+        if constexpr (TRACE) {
+            if (dump) { tr[j] = fmaxf(v[0], 0.f); tr[j + 1] = fmaxf(v[1], 0.f); tr[j + 2] = fmaxf(v[2], 0.f); tr[j + 3] = fmaxf(v[3], 0.f); }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
@@ -236,26 +273,13 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                             tmem_wait_ld();
                             const int f0 = h * NH + c * 32;                 // first output feature of the chunk
                             const float* bsrc = s_bias + li.bias_off + f0;
-                            const float* dsrc = s_dirb + (slot * RMAX + ray_local) * 128 + f0;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 2) {
-                                float v0 = __uint_as_float(r[j]) + bsrc[j];
-                                float v1 = __uint_as_float(r[j + 1]) + bsrc[j + 1];
-                                if (l == 8) { v0 += dsrc[j]; v1 += dsrc[j + 1]; }
-                                if (l == 7) { alpha = fmaf(fmaxf(v0, 0.f), s_aw[f0 + j], alpha); alpha = fmaf(fmaxf(v1, 0.f), s_aw[f0 + j + 1], alpha); }
-                                if (l == 10) {
-                                    const float r0 = fmaxf(v0, 0.f), r1 = fmaxf(v1, 0.f);
-                                    rgb0 = fmaf(r0, s_rw[f0 + j], rgb0); rgb0 = fmaf(r1, s_rw[f0 + j + 1], rgb0);
-                                    rgb1 = fmaf(r0, s_rw[128 + f0 + j], rgb1); rgb1 = fmaf(r1, s_rw[128 + f0 + j + 1], rgb1);
-                                    rgb2 = fmaf(r0, s_rw[256 + f0 + j], rgb2); rgb2 = fmaf(r1, s_rw[256 + f0 + j + 1], rgb2);
-                                }
-                                packed[c * 16 + (j >> 1)] = pack_bf16x2_relu(v0, v1);
-                                if constexpr (TRACE) {      // post-activation values of the first 256 points, [11][256][256]
-                                    if (it == 0) {
-                                        float* tr = trace + ((size_t)l * 256 + slot * 128 + row) * 256 + f0 + j;
-                                        tr[0] = fmaxf(v0, 0.f); tr[1] = fmaxf(v1, 0.f);
-                                    }
-                                }
+                            float* tr = TRACE ? trace + ((size_t)l * 256 + slot * 128 + row) * 256 + f0 : nullptr;
+                            const bool dump = TRACE && it == 0;
+                            switch (l) {                                    // layer kind is warp-uniform: one specialised body per chunk
+                                case 7: epi_convert<1, TRACE>(r, &packed[c * 16], bsrc, nullptr, s_aw + f0, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump); break;
+                                case 8: epi_convert<2, TRACE>(r, &packed[c * 16], bsrc, s_dirb + (slot * RMAX + ray_local) * 128 + f0, nullptr, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump); break;
+                                case 10: epi_convert<3, TRACE>(r, &packed[c * 16], bsrc, nullptr, nullptr, s_rw + f0, alpha, rgb0, rgb1, rgb2, tr, dump); break;
+                                default: epi_convert<0, TRACE>(r, &packed[c * 16], bsrc, nullptr, nullptr, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump); break;
                             }
                         }
                     }
