@@ -57,6 +57,7 @@ SIGNATURES = {
     "inerf_mlp_pack": (_I, [_I, _DIMS, _PARAMS, _P, _P]),
     "inerf_mlp_fwd": (_I, [_I, _DIMS, _PARAMS, _P, _P, _P, _I, _P, _I, _I, _P, _P]),
     "inerf_mlp_fwd_trace": (_I, [_I, _DIMS, _PARAMS, _P, _P, _P, _I, _P, _I, _I, _P, _P, _P]),
+    "inerf_debug_hang_info": (_I, [ctypes.POINTER(ctypes.c_int32)]),
     "inerf_mlp_fwd_embedded": (_I, [_I, _DIMS, _PARAMS, _P, _P, _P, _L, _P, _P]),
 }
 

@@ -96,6 +96,31 @@ struct Bars {
     uint32_t tmem_base;
 };
 
+// Hang diagnostics (trace build only): every mbarrier wait has a ~1 s clock64 budget; the first waiter that
+// runs out records {site code, block, thread, aux...} in a host-mapped buffer and traps.  The production build
+// waits unconditionally.
+__device__ int* g_hang_dev = nullptr;
+
+template <bool DBG>
+__device__ __forceinline__ void wait_or_report(uint64_t* bar, uint32_t parity, int code, int aux0, int aux1) {
+    if constexpr (!DBG) {
+        mbar_wait(bar, parity);
+    } else {
+        const long long t0 = clock64();
+        while (!mbar_try_wait(bar, parity)) {
+            if (clock64() - t0 > 2000000000LL) {
+                int* h = g_hang_dev;
+                if (h && atomicCAS(h, 0, code) == 0) {
+                    h[1] = blockIdx.x; h[2] = threadIdx.x; h[3] = aux0; h[4] = aux1; h[5] = (int)parity;
+                    __threadfence_system();
+                }
+                __nanosleep(1000000);
+                __trap();
+            }
+        }
+    }
+}
+
 struct LayerInfo { int N, bias_off; };
 
 __device__ __forceinline__ LayerInfo layer_info(int l) {
@@ -189,7 +214,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
             for (long long it = blockIdx.x; it < n_iter; it += gridDim.x) {
                 for (int s = 0; s < n_steps; ++s, ++g) {
                     const uint32_t stage = g % NSTAGE, round = g / NSTAGE;
-                    mbar_wait(&bars->wempty[stage], (round & 1) ^ 1);
+                    wait_or_report<TRACE>(&bars->wempty[stage], (round & 1) ^ 1, 101, s, (int)g);
                     const uint32_t bytes = (uint32_t)c_steps[s].n8 * 8u * 128u;
                     mbar_arrive_expect_tx(&bars->wfull[stage], bytes);
                     bulk_g2s(sm + OFF_W + stage * STAGE_BYTES, blob + c_steps[s].offset, bytes, &bars->wfull[stage]);
@@ -210,13 +235,13 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                     if (st.wait & (W_E0 | W_E1)) {
                         if (layer_ctr > 0) {
                             const uint32_t par = (layer_ctr - 1) & 1;
-                            if (st.wait & W_E0) mbar_wait(&bars->ebar[0], par);
-                            if (st.wait & W_E1) mbar_wait(&bars->ebar[1], par);
+                            if (st.wait & W_E0) wait_or_report<TRACE>(&bars->ebar[0], par, 201, s, (int)layer_ctr);
+                            if (st.wait & W_E1) wait_or_report<TRACE>(&bars->ebar[1], par, 202, s, (int)layer_ctr);
                         }
                     }
-                    if (st.wait & W_PE) mbar_wait(&bars->pe_ready, iter_ctr & 1);
+                    if (st.wait & W_PE) wait_or_report<TRACE>(&bars->pe_ready, iter_ctr & 1, 203, s, (int)iter_ctr);
                     const uint32_t stage = g % NSTAGE, round = g / NSTAGE;
-                    mbar_wait(&bars->wfull[stage], round & 1);
+                    wait_or_report<TRACE>(&bars->wfull[stage], round & 1, 204, s, (int)g);
                     tc_fence_after();
                     const uint32_t idesc = umma_idesc_bf16(128, st.n8 * 8);
                     const uint64_t bd = umma_desc_sw128(w_base + stage * STAGE_BYTES);
@@ -258,10 +283,11 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                 const LayerInfo li = layer_info(l);
                 const int NH = li.N >> 1;
                 const uint32_t par = layer_ctr & 1;
-                if (l == 8) mbar_wait(&bars->dirb_ready, iter_ctr & 1);
+                if (l == 8) wait_or_report<TRACE>(&bars->dirb_ready, iter_ctr & 1, 301, l, (int)iter_ctr);
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
-                    mbar_wait(&bars->cbar[h == 0 ? 0 : 2], par);
+                    wait_or_report<TRACE>(&bars->cbar[h == 0 ? 0 : 2], par, 302 + h, l, (int)layer_ctr);
+                    __syncwarp();
                     tc_fence_after();
                     uint32_t packed[64];
                     const int nchunk = NH >> 5;      // 4 (N=256) or 2 (N=128)
@@ -285,7 +311,8 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                     }
                     tc_fence_before();
                     if (l != 10) {
-                        if (h == 0) mbar_wait(&bars->cbar[1], par);      // h1 has finished reading the K-blocks written below
+                        if (h == 0) wait_or_report<TRACE>(&bars->cbar[1], par, 304, l, (int)layer_ctr);
+                        __syncwarp();      // h1 has finished reading the K-blocks written below
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             if (c < nchunk) {
@@ -351,7 +378,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
 #pragma unroll
                 for (int j = 0; j < 32; ++j) pk[sl][j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
             }
-            if (iter_ctr > 0) mbar_wait(&bars->pe_free, (iter_ctr - 1) & 1);
+            if (iter_ctr > 0) wait_or_report<TRACE>(&bars->pe_free, (iter_ctr - 1) & 1, 401, 0, (int)iter_ctr);
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl) {
                 uint8_t* dst = sm + OFF_PE + sl * 16384 + (t >> 3) * 1024 + (t & 7) * 128;
@@ -387,7 +414,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
 #pragma unroll
                     for (int j = 0; j < 27; ++j) enc[j] = 0.f;
                 }
-                if (iter_ctr > 0) mbar_wait(&bars->dirb_free, (iter_ctr - 1) & 1);
+                if (iter_ctr > 0) wait_or_report<TRACE>(&bars->dirb_free, (iter_ctr - 1) & 1, 402, 0, (int)iter_ctr);
                 for (int q2 = 0; q2 < 2 * RMAX; ++q2) {
                     float acc = 0.f;
 #pragma unroll
@@ -518,6 +545,13 @@ int mlp_bf16_pack(const InerfNetDims* d, const float* const* params_host, void* 
     return check_launch("inerf_mlp_pack");
 }
 
+static int* g_hang_host = nullptr;
+
+int mlp_bf16_hang_info(int32_t* out8) {
+    for (int i = 0; i < 8; ++i) out8[i] = g_hang_host ? g_hang_host[i] : 0;
+    return INERF_OK;
+}
+
 int mlp_bf16_launch(const MlpArgs& a, bool embedded, cudaStream_t st) {
     if (embedded)
         return fail(INERF_E_UNSUPPORTED, "bf16 mode is built for the fused (rays, z) entry; FaceNeRF.forward on embedded rows runs in fp32 mode");
@@ -543,6 +577,15 @@ int mlp_bf16_launch(const MlpArgs& a, bool embedded, cudaStream_t st) {
     const long long n_iter = (a.P + 255) / 256;
     const int grid = (int)(n_iter < (long long)num_sms() ? n_iter : (long long)num_sms());
     const int n_rays = (int)(a.P / a.s);
+    if (a.trace) {
+        if (!g_hang_host) {
+            int* dptr = nullptr;
+            if (cudaHostAlloc(&g_hang_host, 64, cudaHostAllocMapped) == cudaSuccess &&
+                cudaHostGetDevicePointer(&dptr, g_hang_host, 0) == cudaSuccess)
+                cudaMemcpyToSymbol(g_hang_dev, &dptr, sizeof(dptr));
+        }
+        if (g_hang_host) for (int i = 0; i < 8; ++i) g_hang_host[i] = 0;
+    }
     if (a.trace) mlp_bf16_kernel<true><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, a.trace);
     else mlp_bf16_kernel<false><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, nullptr);
     return check_launch("inerf_mlp_fwd[bf16]");

@@ -23,6 +23,7 @@ struct MlpArgs {
 
 int mlp_fp32_launch(const MlpArgs& a, bool embedded, cudaStream_t st);
 int mlp_bf16_launch(const MlpArgs& a, bool embedded, cudaStream_t st);
+int mlp_bf16_hang_info(int32_t* out8);
 int mlp_bf16_packed_bytes(const InerfNetDims* d, size_t* bytes);
 int mlp_bf16_pack(const InerfNetDims* d, const float* const* params_host, void* packed, cudaStream_t st);
 

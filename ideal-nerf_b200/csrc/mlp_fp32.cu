@@ -435,6 +435,11 @@ extern "C" int inerf_mlp_fwd_trace(int mode, const InerfNetDims* dims, const flo
     return mlp_bf16_launch(a, false, as_stream(stream));
 }
 
+extern "C" int inerf_debug_hang_info(int32_t* out8) {
+    if (!out8) return fail(INERF_E_ARG, "inerf_debug_hang_info: NULL");
+    return mlp_bf16_hang_info(out8);
+}
+
 extern "C" int inerf_mlp_fwd_embedded(int mode, const InerfNetDims* dims, const float* const* params_host,
                                       const void* packed, const float* cond, const float* x, int64_t p, float* out,
                                       void* stream) {

@@ -185,6 +185,11 @@ int inerf_mlp_fwd_trace(int mode, const InerfNetDims* dims, const float* const* 
                         const float* cond, const float* rays, int ray_stride, const float* z, int n, int s,
                         float* raw, float* trace, void* stream);
 
+/* After a failed inerf_mlp_fwd_trace (the trace build bounds every mbarrier wait to ~1 s and traps): the record
+ * of the first waiter that timed out, {site code, block, thread, aux0, aux1, parity, 0, 0}; all zero otherwise.
+ * HOST pointer to 8 ints. */
+int inerf_debug_hang_info(int32_t* out8);
+
 /* FaceNeRF.forward on already-embedded inputs x (p, in_xyz+in_views) -- the reference module's own
  * call signature (face_nerf.py:40).  out (p, 4). */
 int inerf_mlp_fwd_embedded(int mode, const InerfNetDims* dims, const float* const* params_host,
