@@ -228,18 +228,22 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
             const uint32_t act_base = smem_u32(sm + OFF_ACT), pe_base = smem_u32(sm + OFF_PE), w_base = smem_u32(sm + OFF_W);
             for (long long it = blockIdx.x; it < n_iter; it += gridDim.x, ++iter_ctr) {
                 int cur_layer = 0;
+                uint32_t waited = 0;
                 for (int s = 0; s < n_steps; ++s, ++g) {
                     const Step st = c_steps[s];
-                    if (st.layer != cur_layer) { cur_layer = st.layer; ++layer_ctr; }
-                    // events produced by the epilogue of the previous layer (global layer counter - 1)
-                    if (st.wait & (W_E0 | W_E1)) {
-                        if (layer_ctr > 0) {
-                            const uint32_t par = (layer_ctr - 1) & 1;
-                            if (st.wait & W_E0) wait_or_report<TRACE>(&bars->ebar[0], par, 201, s, (int)layer_ctr);
-                            if (st.wait & W_E1) wait_or_report<TRACE>(&bars->ebar[1], par, 202, s, (int)layer_ctr);
-                        }
+                    if (st.layer != cur_layer) { cur_layer = st.layer; ++layer_ctr; waited = 0; }
+                    // Events produced by the epilogue of the previous layer (global layer counter - 1).  Each event is
+                    // waited at most ONCE per layer: a parity wait repeated after this layer's own C1/C2 commits could
+                    // observe the barrier two phases ahead (the epilogue of THIS layer may already have arrived) and
+                    // block forever.
+                    const uint32_t need = st.wait & ~waited;
+                    waited |= need;
+                    if ((need & (W_E0 | W_E1)) && layer_ctr > 0) {
+                        const uint32_t par = (layer_ctr - 1) & 1;
+                        if (need & W_E0) wait_or_report<TRACE>(&bars->ebar[0], par, 201, s, (int)layer_ctr);
+                        if (need & W_E1) wait_or_report<TRACE>(&bars->ebar[1], par, 202, s, (int)layer_ctr);
                     }
-                    if (st.wait & W_PE) wait_or_report<TRACE>(&bars->pe_ready, iter_ctr & 1, 203, s, (int)iter_ctr);
+                    if (need & W_PE) wait_or_report<TRACE>(&bars->pe_ready, iter_ctr & 1, 203, s, (int)iter_ctr);
                     const uint32_t stage = g % NSTAGE, round = g / NSTAGE;
                     wait_or_report<TRACE>(&bars->wfull[stage], round & 1, 204, s, (int)g);
                     tc_fence_after();
