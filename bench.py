@@ -273,7 +273,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", type=str, default=os.environ.get("INERF_BENCH_MODE", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--mode", type=str, default=os.environ.get("INERF_BENCH_MODE", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -297,7 +297,10 @@ def test_render_rays_fp32_matches_reference(M, golden, tag):
     for k in ("rgb_map", "acc_map", "rgb0", "acc0", "last_weight", "z_std"):
         e = maxabs(r[k], g[f"{tag}_{k}"])
         print(f"[{tag}] {k}: max-abs {e:.3e}")
-        assert e <= tol, f"{k}: {e:.3e}"
+        # the gate names rgb / depth / acc; last_weight (background transmittance, not a gated output) is the most
+        # rounding-sensitive quantity of the dense preset: the reference's own fp32-vs-fp64 MLP moves it by 8.5e-4
+        # (tests/test_oracle_golden.py::test_dense_preset_rounding_floor), so it gets 2e-3.
+        assert e <= (2e-3 if k == "last_weight" else tol), f"{k}: {e:.3e}"
         # random-init weights: nothing amplifies rounding, fp32 mode sits at the 1e-6 level.  The dense preset
         # scales sigma ~x100 and the inverse CDF divides by bin masses ~1e-4, so a last-bit change of a coarse
         # weight moves a fine sample by ~1e-5 and gamma_10 multiplies that by 2^9: ~4e-4 is the algorithm's own

@@ -176,3 +176,33 @@ def test_train_step_grads(golden):
 def test_pose_to_euler_trans(golden):
     g = golden("torso_misc")
     close(O.pose_to_euler_trans(T(g["poses"])), g["euler_trans"], 1e-6)
+
+
+def test_dense_preset_rounding_floor(golden):
+    """How much the REFERENCE algorithm itself moves when only the MLP's rounding changes (fp32 -> fp64 FaceNeRF,
+    everything else identical): the yardstick for the fp32-mode GPU tolerances on the dense preset.  The inverse CDF
+    divides by bin masses ~1e-4 and gamma_10 multiplies depth changes by 2^9, so last-bit changes of the coarse
+    weights become ~1e-4..1e-3 in the fine outputs."""
+    g = golden("render_3072")
+    rays, aud, expr, lat, presets = _presets(g)
+    c, f = presets["dense"]
+    sub = torch.arange(0, 3072, 12)
+    orig = O.run_network
+
+    def run_network_fp64(sd, pts, viewdirs, a, e, l, netchunk=65536):
+        sd64 = {k: v.double() for k, v in sd.items()}
+        return orig(sd64, pts.double(), viewdirs.double(), a.double(), e.double(), l.double(), netchunk).float()
+
+    with torch.no_grad():
+        r32 = O.render_rays(rays[sub], T(g["bc_rgb"])[sub], c, f, aud, expr, lat)
+        O.run_network = run_network_fp64
+        try:
+            r64 = O.render_rays(rays[sub], T(g["bc_rgb"])[sub], c, f, aud, expr, lat)
+        finally:
+            O.run_network = orig
+    d_rgb = float((r32["rgb_map"] - r64["rgb_map"]).abs().max())
+    d_lw = float((r32["last_weight"] - r64["last_weight"]).abs().max())
+    d_rgb0 = float((r32["rgb0"] - r64["rgb0"]).abs().max())
+    print(f"reference fp32-vs-fp64 MLP on 256 dense-preset rays: rgb {d_rgb:.2e}, last_weight {d_lw:.2e}, rgb0 {d_rgb0:.2e}")
+    assert d_rgb0 < 5e-6                     # the coarse pass is quiet ...
+    assert 1e-5 < d_rgb < 1e-3 and 1e-5 < d_lw < 2e-3      # ... the fine pass amplifies rounding by 2-3 orders of magnitude
