@@ -82,7 +82,7 @@ constexpr int OFF_RW = OFF_AW + 1024;                    // rgb_linear.weight 3x
 constexpr int OFF_DIRB = OFF_RW + 1536;                  // [2][RMAX][128] floats
 constexpr int OFF_BAR = OFF_DIRB + 2 * RMAX * 128 * 4;   // mbarriers
 constexpr int SMEM_BYTES = OFF_BAR + 256;
-constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;            // slack for the 1024-byte alignment
+constexpr int SMEM_ALLOC = SMEM_BYTES;
 static_assert(SMEM_ALLOC <= 232448, "shared memory budget");
 
 struct Bars {
@@ -172,8 +172,11 @@ __device__ __forceinline__ void epi_convert(const uint32_t (&r)[32], uint32_t* _
 // ---------------------------------------------------------------------------------------------
 template <bool TRACE>
 __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, int n_steps, int n_rays, float* __restrict__ trace) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // Dynamic shared memory is the only shared allocation of this kernel, so it starts at offset 0 of the CTA's
+    // window: 1024-byte aligned as the 128B-swizzle atoms need.  (No pointer re-alignment arithmetic here: it would
+    // make the compiler lose the shared address space and emit generic LD/ST for every epilogue access.)
+    extern __shared__ __align__(1024) uint8_t sm[];
+    if ((smem_u32(sm) & 1023u) != 0) __trap();
     Bars* bars = reinterpret_cast<Bars*>(sm + OFF_BAR);
     float* s_bias = reinterpret_cast<float*>(sm + OFF_BIAS);
     float* s_aw = reinterpret_cast<float*>(sm + OFF_AW);
@@ -225,6 +228,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
         // ================= MMA issuer ========================================================
         if (lane == 0) {
             uint32_t g = 0, layer_ctr = 0, iter_ctr = 0;
+            long long t_e = 0, t_w = 0, t_pe = 0, t_tot = clock64();      // trace build: where the issuer waits
             const uint32_t act_base = smem_u32(sm + OFF_ACT), pe_base = smem_u32(sm + OFF_PE), w_base = smem_u32(sm + OFF_W);
             for (long long it = blockIdx.x; it < n_iter; it += gridDim.x, ++iter_ctr) {
                 int cur_layer = 0;
@@ -238,14 +242,19 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                     // block forever.
                     const uint32_t need = st.wait & ~waited;
                     waited |= need;
+                    long long c0 = 0;
+                    if constexpr (TRACE) c0 = clock64();
                     if ((need & (W_E0 | W_E1)) && layer_ctr > 0) {
                         const uint32_t par = (layer_ctr - 1) & 1;
                         if (need & W_E0) wait_or_report<TRACE>(&bars->ebar[0], par, 201, s, (int)layer_ctr);
                         if (need & W_E1) wait_or_report<TRACE>(&bars->ebar[1], par, 202, s, (int)layer_ctr);
                     }
+                    if constexpr (TRACE) { const long long c1 = clock64(); t_e += c1 - c0; c0 = c1; }
                     if (need & W_PE) wait_or_report<TRACE>(&bars->pe_ready, iter_ctr & 1, 203, s, (int)iter_ctr);
+                    if constexpr (TRACE) { const long long c1 = clock64(); t_pe += c1 - c0; c0 = c1; }
                     const uint32_t stage = g % NSTAGE, round = g / NSTAGE;
                     wait_or_report<TRACE>(&bars->wfull[stage], round & 1, 204, s, (int)g);
+                    if constexpr (TRACE) t_w += clock64() - c0;
                     tc_fence_after();
                     const uint32_t idesc = umma_idesc_bf16(128, st.n8 * 8);
                     const uint64_t bd = umma_desc_sw128(w_base + stage * STAGE_BYTES);
@@ -265,6 +274,10 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                     if (st.commit & C_PEFREE) umma_commit(&bars->pe_free);
                 }
                 ++layer_ctr;      // the next iteration's L0 is a new layer
+            }
+            if constexpr (TRACE) {      // per-CTA issuer timing after the activation trace: {total, wait E, wait PE, wait weights, iterations}
+                float* t = trace + (size_t)11 * 256 * 256 + blockIdx.x * 8;
+                t[0] = (float)(clock64() - t_tot); t[1] = (float)t_e; t[2] = (float)t_pe; t[3] = (float)t_w; t[4] = (float)iter_ctr;
             }
         }
     } else if (warp >= 4 && warp < 12) {
