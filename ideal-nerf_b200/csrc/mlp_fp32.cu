@@ -56,7 +56,8 @@ __device__ __forceinline__ void store_w_smem(const float (&r)[N / 16], float* ws
 // N = 256: thread owns features {4tn..4tn+3} U {128+4tn..}, N = 128: {4tn..4tn+3}; points 8tm..8tm+7.
 template <int N>
 __device__ void gemm_layer(const float* __restrict__ W, int ldw, const Seg* segs, int nseg,
-                           const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ wsm) {
+                           const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ wsm,
+                           float* __restrict__ save = nullptr) {
     constexpr int NT = N / 32;
     const int tid = threadIdx.x, tn = tid & 31, tm = tid >> 5;
     float acc[NT][8];
@@ -113,14 +114,20 @@ __device__ void gemm_layer(const float* __restrict__ W, int ldw, const Seg* segs
     for (int j = 0; j < NT; ++j) {
         const int n = 4 * tn + (j & 3) + 128 * (j >> 2);
         const float b = __ldg(bias + n);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[j][i] = fmaxf(acc[j][i] + b, 0.f);
         const int sw = (n >> 2) & 15;
-        float4 o0, o1;
-        o0.x = fmaxf(acc[j][0] + b, 0.f); o0.y = fmaxf(acc[j][1] + b, 0.f);
-        o0.z = fmaxf(acc[j][2] + b, 0.f); o0.w = fmaxf(acc[j][3] + b, 0.f);
-        o1.x = fmaxf(acc[j][4] + b, 0.f); o1.y = fmaxf(acc[j][5] + b, 0.f);
-        o1.z = fmaxf(acc[j][6] + b, 0.f); o1.w = fmaxf(acc[j][7] + b, 0.f);
-        *reinterpret_cast<float4*>(out + n * TM + (((2 * tm) ^ sw) << 2)) = o0;
-        *reinterpret_cast<float4*>(out + n * TM + (((2 * tm + 1) ^ sw) << 2)) = o1;
+        *reinterpret_cast<float4*>(out + n * TM + (((2 * tm) ^ sw) << 2)) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+        *reinterpret_cast<float4*>(out + n * TM + (((2 * tm + 1) ^ sw) << 2)) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+    }
+    if (save) {      // training: keep the post-ReLU activations, point-major rows of SAVE_W floats (coalesced 512 B per warp store)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float* row = save + (size_t)(8 * tm + i) * SAVE_W + 4 * tn;
+#pragma unroll
+            for (int jg = 0; jg < NT / 4; ++jg)
+                *reinterpret_cast<float4*>(row + 128 * jg) = make_float4(acc[4 * jg][i], acc[4 * jg + 1][i], acc[4 * jg + 2][i], acc[4 * jg + 3][i]);
+        }
     }
     __syncthreads();
 }
@@ -211,21 +218,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_fp32_kernel(MlpArgs a) {
             }
         }
         __syncthreads();
+        float* sv = a.save ? a.save + (size_t)tile * TM * SAVE_W : nullptr;     // this tile's rows of the activation store
+        if (sv) {                                      // inputs of the dW GEMMs: gamma(p) (64 cols, last = 0) and gamma(v) (32 cols)
+            const int m = tid >> 2, kq = tid & 3;
+            float* row = sv + (size_t)m * SAVE_W + SAVE_PE;
+            for (int k = kq * 24; k < kq * 24 + 24; ++k) row[k] = (k < 64) ? PE[act_idx(k, m)] : DIR[act_idx(k - 64, m)];
+        }
 
         // ---- trunk -----------------------------------------------------------------------------
         Seg sg[2];
         sg[0] = {PE, 63, 0};
-        gemm_layer<256>(a.w[0], 63 + C, sg, 1, a.cond + cl.pts(0), H0, WS);
+        gemm_layer<256>(a.w[0], 63 + C, sg, 1, a.cond + cl.pts(0), H0, WS, sv);
         float* cur = H0;
         float* nxt = H1;
         for (int l = 1; l < 8; ++l) {
             if (l == 5) {
                 sg[0] = {PE, 63, 0};
                 sg[1] = {cur, 256, 63 + C};
-                gemm_layer<256>(a.w[2 * l], 319 + C, sg, 2, a.cond + cl.pts(l), nxt, WS);
+                gemm_layer<256>(a.w[2 * l], 319 + C, sg, 2, a.cond + cl.pts(l), nxt, WS, sv ? sv + l * 256 : nullptr);
             } else {
                 sg[0] = {cur, 256, 0};
-                gemm_layer<256>(a.w[2 * l], 256, sg, 1, a.cond + cl.pts(l), nxt, WS);
+                gemm_layer<256>(a.w[2 * l], 256, sg, 1, a.cond + cl.pts(l), nxt, WS, sv ? sv + l * 256 : nullptr);
             }
             float* t = cur; cur = nxt; nxt = t;
         }
@@ -238,11 +251,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_fp32_kernel(MlpArgs a) {
         // ---- view branch -----------------------------------------------------------------------
         sg[0] = {cur, 256, 0};
         sg[1] = {DIR, 27, 256};
-        gemm_layer<128>(a.w[P_VIEWS_W], 283 + a.dim_expr, sg, 2, a.cond + cl.views(0), nxt, WS);
+        gemm_layer<128>(a.w[P_VIEWS_W], 283 + a.dim_expr, sg, 2, a.cond + cl.views(0), nxt, WS, sv ? sv + 2048 : nullptr);
         sg[0] = {nxt, 128, 0};
-        gemm_layer<128>(a.w[P_VIEWS_W + 2], 128, sg, 1, a.cond + cl.views(1), cur, WS);
+        gemm_layer<128>(a.w[P_VIEWS_W + 2], 128, sg, 1, a.cond + cl.views(1), cur, WS, sv ? sv + 2048 + 128 : nullptr);
         sg[0] = {cur, 128, 0};
-        gemm_layer<128>(a.w[P_VIEWS_W + 4], 128, sg, 1, a.cond + cl.views(2), nxt, WS);
+        gemm_layer<128>(a.w[P_VIEWS_W + 4], 128, sg, 1, a.cond + cl.views(2), nxt, WS, sv ? sv + 2048 + 256 : nullptr);
         small_head<3>(a.w[P_RGB_W], 128, nxt, RED);
         if (tid < 3 * TM) {
             const int o = tid / TM, m = tid - o * TM;
@@ -433,6 +446,58 @@ extern "C" int inerf_mlp_fwd_trace(int mode, const InerfNetDims* dims, const flo
     a.rays = rays; a.ray_stride = ray_stride; a.z = z; a.s = s;
     a.P = (long long)n * s; a.out = raw; a.packed = packed; a.trace = trace;
     return mlp_bf16_launch(a, false, as_stream(stream));
+}
+
+extern "C" int inerf_mlp_train_sizes(const InerfNetDims* dims, int64_t n_points, size_t* acts_floats, size_t* deltas_floats,
+                                     size_t* scratch_bytes) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (n_points < 0 || !acts_floats || !deltas_floats || !scratch_bytes) return fail(INERF_E_ARG, "inerf_mlp_train_sizes: bad argument");
+    const size_t p64 = (size_t)((n_points + 63) / 64) * 64;
+    *acts_floats = p64 * SAVE_W;
+    *deltas_floats = p64 * DELTA_W;
+    *scratch_bytes = mlp_fp32_bwd_args_bytes();
+    return INERF_OK;
+}
+
+extern "C" int inerf_mlp_fwd_train(const InerfNetDims* dims, const float* const* params_host, const float* cond,
+                                   const float* rays, int ray_stride, const float* z, int n, int s, const float* x,
+                                   int64_t p_embedded, float* raw, float* acts, void* stream) {
+    MlpArgs a{};
+    int rc = fill_args(a, dims, params_host, cond);
+    if (rc) return rc;
+    if (!raw || !acts) return fail(INERF_E_ARG, "inerf_mlp_fwd_train: NULL pointer");
+    if (((uintptr_t)raw | (uintptr_t)acts) & 15) return fail(INERF_E_ALIGN, "inerf_mlp_fwd_train: raw/acts must be 16-byte aligned");
+    a.out = raw; a.save = acts;
+    if (x) {
+        if (p_embedded <= 0) return p_embedded == 0 ? INERF_OK : fail(INERF_E_SHAPE, "inerf_mlp_fwd_train: p < 0");
+        a.x = x; a.P = p_embedded; a.s = 1;
+        return mlp_fp32_launch(a, true, as_stream(stream));
+    }
+    if (n < 0 || s <= 0 || ray_stride < 11) return fail(INERF_E_SHAPE, "inerf_mlp_fwd_train: bad n/s/ray_stride");
+    if (n == 0) return INERF_OK;
+    if (!rays || !z) return fail(INERF_E_ARG, "inerf_mlp_fwd_train: NULL pointer");
+    a.rays = rays; a.ray_stride = ray_stride; a.z = z; a.s = s; a.P = (long long)n * s;
+    return mlp_fp32_launch(a, false, as_stream(stream));
+}
+
+extern "C" int inerf_mlp_bwd(const InerfNetDims* dims, const float* const* params_host, float* const* grads_host,
+                             const float* aud, const float* expr, const float* latent, const float* acts, float* deltas,
+                             const float* d_raw, int64_t n_points, float* d_cond, void* scratch, void* stream) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (n_points < 0) return fail(INERF_E_SHAPE, "inerf_mlp_bwd: n_points < 0");
+    if (n_points == 0) return INERF_OK;
+    if (!params_host || !grads_host || !acts || !deltas || !d_raw || !scratch) return fail(INERF_E_ARG, "inerf_mlp_bwd: NULL pointer");
+    for (int i = 0; i < INERF_N_PARAMS; ++i)
+        if (!params_host[i] || !grads_host[i]) return fail(INERF_E_ARG, "inerf_mlp_bwd: NULL parameter/gradient pointer");
+    const int C = dims->dim_aud + dims->dim_expr + dims->dim_latent;
+    if (C > 0 && !d_cond) return fail(INERF_E_ARG, "inerf_mlp_bwd: d_cond is NULL");
+    if ((dims->dim_aud > 0 && !aud) || (dims->dim_expr > 0 && !expr) || (dims->dim_latent > 0 && !latent))
+        return fail(INERF_E_ARG, "inerf_mlp_bwd: conditioning vector missing for a non-zero dim");
+    if (((uintptr_t)acts | (uintptr_t)deltas | (uintptr_t)d_raw) & 15) return fail(INERF_E_ALIGN, "inerf_mlp_bwd: acts/deltas/d_raw must be 16-byte aligned");
+    return mlp_fp32_bwd_launch(dims, params_host, grads_host, aud, expr, latent, acts, deltas, d_raw, n_points, d_cond, scratch,
+                               as_stream(stream));
 }
 
 extern "C" int inerf_debug_hang_info(int32_t* out8) {

@@ -95,19 +95,43 @@ class FaceNeRF(nn.Module):
 
 
 class _MlpFn(torch.autograd.Function):
+    """run_network + FaceNeRF as one op.  Inference: one fused kernel in the module's mlp_mode.  Training (any
+    parameter or conditioning vector requires grad): the fp32 kernel keeps its activations and backward() runs the
+    analytic gradient kernels (csrc/mlp_fp32_bwd.cu)."""
+
     @staticmethod
     def forward(ctx, net, embedded, a, b, aud, expr, latent, *params):
         mode = net._mode()
         pd = [p.detach() for p in params]
-        cond = ops.fold_cond(net._dims, pd, aud, expr, latent)
+        f = lambda t: None if t is None else ops.f32c(t.detach(), "conditioning")
+        aud_d, expr_d, lat_d = f(aud), f(expr), f(latent)
+        cond = ops.fold_cond(net._dims, pd, aud_d, expr_d, lat_d)
+        train = torch.is_grad_enabled() and any(ctx.needs_input_grad[4:])
+        if train:
+            if mode != _lib.INERF_MLP_FP32:
+                raise NotImplementedError("training runs in mlp_mode='fp32' (the bf16 tensor-core kernel is forward-only)")
+            out, acts, n_points = ops.mlp_fwd_train(net._dims, pd, cond, x=a) if embedded else \
+                ops.mlp_fwd_train(net._dims, pd, cond, rays=a, z=b)
+            ctx.net, ctx.n_points, ctx.has = net, n_points, (aud is not None, expr is not None, latent is not None)
+            ctx.save_for_backward(acts, *[t for t in (aud_d, expr_d, lat_d) if t is not None], *pd)
+            return out
         packed = net.packed_weights(params)
         if embedded:
-            out = ops.mlp_fwd_embedded(mode, net._dims, pd, packed, cond, a)
-        else:
-            out = ops.mlp_fwd(mode, net._dims, pd, packed, cond, a, b)
-        ctx.net = net
-        return out
+            return ops.mlp_fwd_embedded(mode, net._dims, pd, packed, cond, a)
+        return ops.mlp_fwd(mode, net._dims, pd, packed, cond, a, b)
 
     @staticmethod
     def backward(ctx, g):
-        raise NotImplementedError("FaceNeRF backward kernels are not built yet (forward/render only)")
+        saved = list(ctx.saved_tensors)
+        acts = saved.pop(0)
+        aud = saved.pop(0) if ctx.has[0] else None
+        expr = saved.pop(0) if ctx.has[1] else None
+        latent = saved.pop(0) if ctx.has[2] else None
+        params = saved
+        d = ctx.net._dims
+        grads, d_cond = ops.mlp_bwd(d, params, aud, expr, latent, acts, g, ctx.n_points)
+        da, de = d.dim_aud, d.dim_expr
+        g_aud = d_cond[:da] if aud is not None else None
+        g_expr = d_cond[da:da + de] if expr is not None else None
+        g_lat = d_cond[da + de:da + de + d.dim_latent] if latent is not None else None
+        return (None, None, None, None, g_aud, g_expr, g_lat, *grads)

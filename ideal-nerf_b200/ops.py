@@ -311,6 +311,44 @@ def mlp_fwd(mode, dims, params, packed, cond, rays, z):
     return raw
 
 
+def mlp_fwd_train(dims, params, cond, rays=None, z=None, x=None):
+    """fp32 forward that keeps the activations for mlp_bwd.  Returns (raw, acts, n_points)."""
+    if x is None:
+        rays, z = f32c(rays, "rays"), f32c(z, "z_vals")
+        n, s = z.shape
+        n_points, dev, out_shape = n * s, z.device, (n, s, 4)
+    else:
+        x = f32c(x, "x")
+        n, s, n_points, dev, out_shape = 0, 1, x.shape[0], x.device, (x.shape[0], 4)
+    sizes = [ctypes.c_size_t() for _ in range(3)]
+    check(_lib.lib().inerf_mlp_train_sizes(ctypes.byref(dims), n_points, *[ctypes.byref(v) for v in sizes]), "inerf_mlp_train_sizes")
+    raw = torch.empty(out_shape, device=dev)
+    acts = torch.empty((sizes[0].value,), device=dev)
+    arr = param_array(params)
+    with torch.cuda.device(dev):
+        call("inerf_mlp_fwd_train", _lib.lib().inerf_mlp_fwd_train, ctypes.byref(dims), arr, ptr(cond), ptr(rays),
+             rays.shape[1] if rays is not None else 11, ptr(z), n, s, ptr(x), n_points if x is not None else 0, ptr(raw),
+             ptr(acts), stream())
+    return raw, acts, n_points
+
+
+def mlp_bwd(dims, params, aud, expr, latent, acts, d_raw, n_points):
+    """Analytic backward of FaceNeRF (fp32).  Returns (grads[26] in nn.Linear layout, d_cond [aud|expr|latent])."""
+    dev = acts.device
+    sizes = [ctypes.c_size_t() for _ in range(3)]
+    check(_lib.lib().inerf_mlp_train_sizes(ctypes.byref(dims), n_points, *[ctypes.byref(v) for v in sizes]), "inerf_mlp_train_sizes")
+    deltas = torch.empty((sizes[1].value,), device=dev)
+    scratch = torch.empty((sizes[2].value,), device=dev, dtype=torch.uint8)
+    grads = [torch.zeros_like(p) for p in params]
+    d_cond = torch.zeros((max(1, dims.dim_aud + dims.dim_expr + dims.dim_latent),), device=dev)
+    d_raw = f32c(d_raw, "d_raw").reshape(-1, 4)
+    parr, garr = param_array(params), param_array(grads)
+    with torch.cuda.device(dev):
+        call("inerf_mlp_bwd", _lib.lib().inerf_mlp_bwd, ctypes.byref(dims), parr, garr, ptr(aud), ptr(expr), ptr(latent),
+             ptr(acts), ptr(deltas), ptr(d_raw), n_points, ptr(d_cond), ptr(scratch), stream())
+    return grads, d_cond
+
+
 def mlp_fwd_trace(mode, dims, params, packed, cond, rays, z):
     """bf16 kernel with the per-layer activation trace of the first 256 points: returns (raw, trace[11,256,256])."""
     rays, z = f32c(rays, "rays"), f32c(z, "z_vals")

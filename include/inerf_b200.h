@@ -185,6 +185,26 @@ int inerf_mlp_fwd_trace(int mode, const InerfNetDims* dims, const float* const* 
                         const float* cond, const float* rays, int ray_stride, const float* z, int n, int s,
                         float* raw, float* trace, void* stream);
 
+/* ---- training (fp32 mode): forward that keeps activations + analytic backward ------------------------------- */
+
+/* Buffer sizes for n_points = n*s points: acts (floats), deltas (floats), scratch (bytes, device). */
+int inerf_mlp_train_sizes(const InerfNetDims* dims, int64_t n_points, size_t* acts_floats, size_t* deltas_floats,
+                          size_t* scratch_bytes);
+
+/* inerf_mlp_fwd (fused entry: rays/z) or inerf_mlp_fwd_embedded (x != NULL, p_embedded rows) in fp32 mode that also
+ * stores every post-ReLU activation and both encodings in `acts` for inerf_mlp_bwd. */
+int inerf_mlp_fwd_train(const InerfNetDims* dims, const float* const* params_host, const float* cond, const float* rays,
+                        int ray_stride, const float* z, int n, int s, const float* x, int64_t p_embedded, float* raw,
+                        float* acts, void* stream);
+
+/* Backward of FaceNeRF: what torch.autograd computes for models/face_nerf.py:40-80 inside the reference's
+ * loss.backward() (audio_exp_nerf.py:549).  d_raw (n_points,4).  grads_host: INERF_N_PARAMS device pointers (host array)
+ * to ZERO-INITIALISED gradient tensors in nn.Linear layout; d_cond: zero-initialised [dim_aud+dim_expr+dim_latent] =
+ * [d_aud | d_expr | d_latent].  deltas / scratch: workspaces sized by inerf_mlp_train_sizes. */
+int inerf_mlp_bwd(const InerfNetDims* dims, const float* const* params_host, float* const* grads_host, const float* aud,
+                  const float* expr, const float* latent, const float* acts, float* deltas, const float* d_raw,
+                  int64_t n_points, float* d_cond, void* scratch, void* stream);
+
 /* After a failed inerf_mlp_fwd_trace (the trace build bounds every mbarrier wait to ~1 s and traps): the record
  * of the first waiter that timed out, {site code, block, thread, aux0, aux1, parity, 0, 0}; all zero otherwise.
  * HOST pointer to 8 ints. */

@@ -467,3 +467,89 @@ def test_bf16_rejects_small_s_and_embedded(M):
     z = M.ops.sample_coarse(rays, 7)
     with pytest.raises(RuntimeError, match="32 samples"):
         net.query(rays, z, b["aud"].to(DEV), b["expr"].to(DEV), b["latent"].to(DEV))
+
+
+# ------------------------------------------------------------------------------------------------
+# training step (config 3): loss + gradients against the reference's autograd
+# ------------------------------------------------------------------------------------------------
+def test_face_nerf_backward_vs_autograd(M):
+    """FaceNeRF.forward on embedded rows: every gradient against torch.autograd of the oracle (ragged tile, 203 rows)."""
+    gen = torch.Generator().manual_seed(2)
+    sd = O.init_face_nerf(9)
+    P = 203
+    x = torch.cat([O.positional_encoding(torch.randn(P, 3, generator=gen) * 0.5, 10),
+                   O.positional_encoding(torch.nn.functional.normalize(torch.randn(P, 3, generator=gen), dim=-1), 4)], -1)
+    aud, expr, lat = torch.randn(64, generator=gen), torch.randn(76, generator=gen), torch.ones(32)
+    gout = torch.randn(P, 4, generator=gen)
+    sd_r = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    a_r, e_r, l_r = (t.clone().requires_grad_(True) for t in (aud, expr, lat))
+    (O.face_nerf_forward(sd_r, x, a_r, e_r, l_r) * gout).sum().backward()
+    net = head_net(M, sd)
+    a_g, e_g, l_g = (t.to(DEV).requires_grad_(True) for t in (aud, expr, lat))
+    out = net(x.to(DEV), a_g, e_g, l_g)
+    close(out, O.face_nerf_forward(sd, x, aud, expr, lat), 2e-5, "train-mode forward")
+    (out * gout.to(DEV)).sum().backward()
+    close(a_g.grad, a_r.grad, 2e-4, "d_aud"); close(e_g.grad, e_r.grad, 2e-4, "d_expr"); close(l_g.grad, l_r.grad, 2e-4, "d_latent")
+    for name, p in net.named_parameters():
+        ref = sd_r[name].grad
+        if ref is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name     # feature_linear: never applied
+            continue
+        tol = 2e-5 * max(1.0, float(ref.abs().max()))
+        close(p.grad, ref, tol, f"grad {name}")
+
+
+def test_train_step_grads_golden(M, golden):
+    """32 rays through coarse+fine render_rays, loss of audio_exp_nerf.py:540-548, backward: against the gradients the
+    unmodified reference produced (tests/golden/train_step.npz)."""
+    g, tr = golden("render_3072"), golden("train_step")
+    net = _preset_nets(M, g, "dense").train()
+    idx = C(tr["idx"])
+    aud, expr, lat = (C(g[k]).clone().requires_grad_(True) for k in ("aud", "expr", "latent"))
+    r = net.render_rays(C(g["rays"])[idx], C(g["bc_rgb"])[idx], aud, None, lat, expr, perturb=0.)
+    tgt = C(g["target"])[idx]
+    loss = torch.mean((r["rgb_map"] - tgt) ** 2) + torch.mean((r["rgb0"] - tgt) ** 2) + 10 * 0.0005 * torch.norm(lat)
+    loss.backward()
+    close(loss, tr["loss"], 2e-5, "loss")
+    close(aud.grad, tr["d_aud"], 2e-5, "d_aud"); close(expr.grad, tr["d_expr"], 2e-5, "d_expr"); close(lat.grad, tr["d_latent"], 2e-5, "d_latent")
+    nets = {"c": net.face_nerf_coarse, "f": net.face_nerf_fine}
+    checked = 0
+    for key in tr:
+        kind, _, name = key.partition(":")
+        if kind not in ("norm", "grad", "samp"):
+            continue
+        tag, _, pname = name.partition(".")
+        gr = dict(nets[tag].named_parameters())[pname].grad
+        if kind == "norm":
+            assert abs(float(gr.double().norm()) - float(tr[key])) <= 2e-3 * max(1e-6, float(tr[key])) + 1e-8, key
+        elif kind == "grad":
+            close(gr, tr[key], 5e-4 * max(1e-3, float(np.abs(tr[key]).max())), key)
+        else:
+            close(gr.reshape(-1)[::97], tr[key], 5e-4 * max(1e-3, float(np.abs(tr[key]).max())), key)
+        checked += 1
+    assert checked > 40
+
+
+def test_training_loop_reduces_loss(M):
+    """A few Adam steps (lrate 3e-4 x10, audio_exp_nerf.py:493) on a fixed 256-ray batch: the loss must go down."""
+    b = O.synthetic_train_batch(0)
+    idx = torch.arange(0, 3072, 12)
+    args = M.default_args(dim_aud=64, dim_expr=76, perturb=1.0, N_samples=64, N_importance=128)
+    net = M.Network(450, 450, 1200., O.NEAR, O.FAR, 8192, None, 64, 128, args=args)
+    torch.manual_seed(0)
+    net.apply(M.init_weights)
+    net = net.to(DEV).train()
+    lat = torch.ones(32, device=DEV, requires_grad=True)
+    opt = torch.optim.Adam(list(net.parameters()) + [lat], lr=3e-3, betas=(0.9, 0.999))
+    rays, bc, tgt = b["rays"][idx].to(DEV), b["bc_rgb"][idx].to(DEV), b["target"][idx].to(DEV)
+    aud, expr = b["aud"].to(DEV), b["expr"].to(DEV)
+    losses = []
+    for _ in range(6):
+        opt.zero_grad()
+        r = net.render_rays(rays, bc, aud, None, lat, expr)
+        loss = torch.mean((r["rgb_map"] - tgt) ** 2) + torch.mean((r["rgb0"] - tgt) ** 2) + 10 * 0.0005 * torch.norm(lat)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    print("losses", losses)
+    assert losses[-1] < losses[0] and all(np.isfinite(losses))
