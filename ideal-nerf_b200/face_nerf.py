@@ -106,7 +106,7 @@ class _MlpFn(torch.autograd.Function):
         f = lambda t: None if t is None else ops.f32c(t.detach(), "conditioning")
         aud_d, expr_d, lat_d = f(aud), f(expr), f(latent)
         cond = ops.fold_cond(net._dims, pd, aud_d, expr_d, lat_d)
-        train = torch.is_grad_enabled() and any(ctx.needs_input_grad[4:])
+        train = any(ctx.needs_input_grad[4:])      # all False under torch.no_grad(); grad mode itself is off inside forward()
         if train:
             if mode != _lib.INERF_MLP_FP32:
                 raise NotImplementedError("training runs in mlp_mode='fp32' (the bf16 tensor-core kernel is forward-only)")
