@@ -136,6 +136,49 @@ def build_network(mode, dev):
     return M, net, fr, cam
 
 
+def train_step_bench(M, dev, steps):
+    """BASELINE.json config 3: N_rand=3072 rays (64+128 samples), loss of audio_exp_nerf.py:540-548, backward through
+    compositing + both FaceNeRFs, Adam(lr=3e-4) step.  fp32 kernels (the bf16 tensor-core kernel is forward-only)."""
+    from ideal_nerf_b200 import synthetic as S, ops
+    cam, fr = S.camera(), S.frame_inputs(0)
+    a = M.default_args(dim_aud=64, dim_expr=76, perturb=1.0, mlp_mode="fp32", N_samples=S1, N_importance=S_IMP)
+    net = M.Network(H, W, cam["focal"], S.NEAR, S.FAR, 8192, None, S1, S_IMP, args=a)
+    torch.manual_seed(4321)
+    net.apply(M.init_weights)
+    net = net.to(dev).train()
+    g = torch.Generator().manual_seed(5)
+    idx = torch.randperm(N_RAYS, generator=g)[:3072].to(dev)
+    rays = ops.get_rays_packed(H, W, cam["focal"], cam["c2w"].to(dev), S.NEAR, S.FAR)[idx].contiguous()
+    bc, tgt = fr["bc_rgb"].to(dev)[idx].contiguous(), torch.rand(3072, 3, generator=g).to(dev)
+    aud, expr = fr["aud"].to(dev), fr["expr"].to(dev)
+    lat = torch.ones(32, device=dev, requires_grad=True)
+    opt = torch.optim.Adam(list(net.parameters()) + [lat], lr=3e-4, betas=(0.9, 0.999))
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        r = net.render_rays(rays, bc, aud, None, lat, expr)
+        loss = torch.mean((r["rgb_map"] - tgt) ** 2) + torch.mean((r["rgb0"] - tgt) ** 2) + 10 * 0.0005 * torch.norm(lat)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ops.LAUNCHES["count"] = 0
+    with ops.kernel_timing() as kt:
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"rays_per_s": 3072 / (ms * 1e-3), "ms_per_step": ms, "n_rand": 3072, "mlp_mode": "fp32", "optimizer": "Adam lr=3e-4",
+            "loss": float(loss), "gpu_launches_per_step": ops.LAUNCHES["count"] / steps,
+            "kernels_ms_per_step": {k: round(v[1] / steps, 3) for k, v in kt.summary().items()}}
+
+
 def run_ours(args):
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -257,6 +300,8 @@ def run_ours(args):
                                    "launches": n_cmp, "kernel_ms_total": cmp_ms},
             "kernels_ms": {k: round(v[1], 3) for k, v in ksum.items()},
         }
+        if world == 1 and not args.no_train:
+            line["train_step"] = train_step_bench(M, dev, 3)
         if world == 1 and not args.no_cpu_baseline:
             v, dt, cores = cpu_reference_rays_per_s(3072, 2, 1)
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
@@ -275,6 +320,7 @@ def main():
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", type=str, default=os.environ.get("INERF_BENCH_MODE", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-train", dest="no_train", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
