@@ -1,0 +1,60 @@
+"""World-size-2 checks of the ray partition + image gather (gloo on CPU; the render kernels themselves are GPU-only)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_rays, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ideal_nerf_b200.frame import FrameRenderer, band
+    lo, hi = band(n_rays, rank, world)
+    full = torch.arange(n_rays * 3, dtype=torch.float32).reshape(n_rays, 3)     # the "rendered image"
+    fr = FrameRenderer(network=None, rank=rank, world=world)
+    out = fr.gather_image(full[lo:hi].clone(), n_rays)
+    if rank == 0:
+        q.put((tuple(out.shape), bool(torch.equal(out, full))))
+    else:
+        assert out is None
+    # max-over-ranks timing reduction used by bench.py
+    t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    assert float(t) == world
+    dist.destroy_process_group()
+
+
+def test_band_partition_covers_every_ray_once():
+    from ideal_nerf_b200.frame import band
+    for n in (202500, 3072, 7, 1):
+        for world in (1, 2, 3, 4, 8):
+            spans = [band(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert all(0 <= hi - lo <= (n + world - 1) // world for lo, hi in spans)
+
+
+def test_gather_image_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    for n_rays in (202500, 11):           # even split, and a ragged tail (6 + 5)
+        procs = [ctx.Process(target=_worker, args=(r, 2, port, n_rays, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(timeout=120)
+            assert p.exitcode == 0
+        shape, ok = q.get(timeout=10)
+        assert shape == (n_rays, 3) and ok
+        port = _free_port()
