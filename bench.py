@@ -205,6 +205,7 @@ def run_ours(args):
     frames = world                                   # frames per step (weak scaling: 202 500 rays per rank per step)
     lo, hi = band(N_RAYS, rank, world)
 
+    @torch.no_grad()
     def step_resident():
         out = None
         for _ in range(frames):
@@ -215,6 +216,7 @@ def run_ours(args):
     out_h = torch.empty((N_RAYS, 3)).pin_memory()
     h2d = sum(host[k].numel() * 4 for k in host)
 
+    @torch.no_grad()
     def step_e2e():
         """Public API with HOST buffers: H2D of the frame's inputs, render, gather, D2H of the image."""
         for _ in range(frames):
