@@ -85,13 +85,19 @@ class FaceNeRF(nn.Module):
     def forward(self, x, aud, expr=None, latent_code=None):
         """x (P, 63+27) already embedded, as in face_nerf.py:40.  Returns (P, 4) = [rgb, sigma] pre-activation."""
         params = self._prep(aud, expr, latent_code)
-        return _MlpFn.apply(self, True, x, None, aud, expr, latent_code, *params)
+        return _MlpFn.apply(self, (True, self._wants_grad(params, aud, expr, latent_code)), x, None, aud, expr, latent_code, *params)
 
     # -- fused entry used by render_rays ----------------------------------------------------------
     def query(self, rays, z_vals, aud, expr=None, latent_code=None):
         """run_network on the points o + d*z of packed rays (n,11) / depths (n,s): returns raw (n,s,4)."""
         params = self._prep(aud, expr, latent_code)
-        return _MlpFn.apply(self, False, rays, z_vals, aud, expr, latent_code, *params)
+        return _MlpFn.apply(self, (False, self._wants_grad(params, aud, expr, latent_code)), rays, z_vals, aud, expr, latent_code, *params)
+
+    @staticmethod
+    def _wants_grad(params, *cond):
+        """Training path only when autograd is recording (grad mode is always off INSIDE Function.forward, and
+        needs_input_grad ignores torch.no_grad(), so this is decided here)."""
+        return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in list(params) + list(cond))
 
 
 class _MlpFn(torch.autograd.Function):
@@ -100,13 +106,13 @@ class _MlpFn(torch.autograd.Function):
     analytic gradient kernels (csrc/mlp_fp32_bwd.cu)."""
 
     @staticmethod
-    def forward(ctx, net, embedded, a, b, aud, expr, latent, *params):
+    def forward(ctx, net, flags, a, b, aud, expr, latent, *params):
+        embedded, train = flags
         mode = net._mode()
         pd = [p.detach() for p in params]
         f = lambda t: None if t is None else ops.f32c(t.detach(), "conditioning")
         aud_d, expr_d, lat_d = f(aud), f(expr), f(latent)
         cond = ops.fold_cond(net._dims, pd, aud_d, expr_d, lat_d)
-        train = any(ctx.needs_input_grad[4:])      # all False under torch.no_grad(); grad mode itself is off inside forward()
         if train:
             if mode != _lib.INERF_MLP_FP32:
                 raise NotImplementedError("training runs in mlp_mode='fp32' (the bf16 tensor-core kernel is forward-only)")
