@@ -40,7 +40,15 @@ __device__ __forceinline__ float reduce8(float (&v)[8], int lane) {
     return c;
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return __fdiv_rn(1.0f, 1.0f + expf(-x)); }
+// exp / sigmoid through the SFU (ex2.approx, rcp.approx): <= 2 ulp on ex2 plus the rounding of x*log2(e), i.e. an absolute
+// error below 3e-7 on alpha and on the colours -- three orders under the 1e-3 gate, and 60 fewer issue slots per
+// 32 samples than the IEEE expf + division (the kernel was issue bound, not HBM bound, with those).
+__device__ __forceinline__ float fast_exp(float x) {                                             // FMUL + MUFU.EX2
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + fast_exp(-x)); }
 
 struct Sample {
     float alpha, q, dist, s;   // s = sigma + noise (pre-relu)
@@ -51,7 +59,7 @@ __device__ __forceinline__ Sample make_sample(float sigma, float noise, float z,
     Sample o;
     o.s = sigma + noise;
     o.dist = (last ? 1e10f : (znext - z)) * norm;
-    float e = expf(-(fmaxf(o.s, 0.0f) + 1e-6f) * o.dist);
+    float e = fast_exp(-(fmaxf(o.s, 0.0f) + 1e-6f) * o.dist);
     o.alpha = valid ? 1.0f - e : 0.0f;
     o.q = valid ? (1.0f - o.alpha) + 1e-10f : 1.0f;
     return o;
@@ -135,6 +143,104 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(
     float acc_t = __shfl_sync(0xffffffffu, tot, 16);
     float depth_t = __shfl_sync(0xffffffffu, tot, 12);
     int q = lane >> 2;
+    if ((lane & 3) == 0) {
+        if (q < 3) rgb[ray * 3 + q] = white_bkgd ? tot + (1.0f - acc_t) : tot;
+        else if (q == 3) {
+            depth[ray] = depth_t;
+            disp[ray] = __fdiv_rn(1.0f, fmaxf(1e-10f, __fdiv_rn(depth_t, acc_t)));
+        } else if (q == 4) acc[ray] = acc_t;
+        else if (rgb_fg) rgb_fg[ray * 3 + (q - 5)] = tot;
+    }
+}
+
+// Forward for even S (every production shape: 64, 192): lane l owns the two ADJACENT samples 2l, 2l+1 of each
+// 64-sample chunk, so raw arrives as one 256-bit load per lane (LDG.256, 1 KB contiguous per warp), z / weights as
+// 64-bit accesses, and the transmittance scan runs once per 64 samples on the per-lane product q_a*q_b -- half the
+// shuffles and selects per sample of the one-sample-per-lane form above (which stays for odd S).
+struct Raw2 { float4 a, b; };
+
+__device__ __forceinline__ Raw2 ldg_stream8(const float4* p) {
+    Raw2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ float2 ldg_stream2(const float* p) {
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) composite_fwd2_kernel(
+    const float4* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d, int d_stride,
+    const float* __restrict__ bc_rgb, const float* __restrict__ noise, int n, int s, int white_bkgd,
+    float* __restrict__ rgb, float* __restrict__ disp, float* __restrict__ acc, float* __restrict__ depth,
+    float* __restrict__ weights, float* __restrict__ rgb_fg) {
+    const int lane = threadIdx.x & 31;
+    const int ray = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ray >= n) return;
+    const size_t base = (size_t)ray * s;
+
+    Raw2 rv[C];
+    float2 zv[C], nv[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int i = c * 64 + 2 * lane;                       // s is even: i < s  <=>  i + 1 < s
+        const bool ok = i < s;
+        if (ok) {
+            rv[c] = ldg_stream8(raw + base + i);
+            zv[c] = ldg_stream2(z + base + i);
+            nv[c] = noise ? ldg_stream2(noise + base + i) : make_float2(0.f, 0.f);
+        } else {
+            rv[c].a = rv[c].b = make_float4(0.f, 0.f, 0.f, 0.f);
+            zv[c] = nv[c] = make_float2(0.f, 0.f);
+        }
+    }
+    const float* dptr = rays_d + (size_t)ray * d_stride;
+    const float dx = dptr[0], dy = dptr[1], dz = dptr[2];
+    const float norm = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float bcr = bc_rgb[ray * 3], bcg = bc_rgb[ray * 3 + 1], bcb = bc_rgb[ray * 3 + 2];
+
+    float carry = 1.0f;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int i = c * 64 + 2 * lane;
+        const bool valid = i < s, last_b = i + 1 == s - 1;     // the ray's last sample is always a `b`
+        float znext = __shfl_down_sync(0xffffffffu, zv[c].x, 1);
+        if (c + 1 < C) {
+            const float z0 = __shfl_sync(0xffffffffu, zv[c + 1 < C ? c + 1 : c].x, 0);
+            if (lane == 31) znext = z0;
+        }
+        const Sample sa = make_sample(rv[c].a.w, nv[c].x, zv[c].x, zv[c].y, norm, false, valid);
+        const Sample sb = make_sample(rv[c].b.w, nv[c].y, zv[c].y, znext, norm, last_b, valid);
+        const float incl = warp_scan_mul(sa.q * sb.q, lane);
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.0f;
+        const float Ta = carry * excl;
+        const float Tb = Ta * sa.q;
+        carry *= __shfl_sync(0xffffffffu, incl, 31);
+        const float wa = sa.alpha * Ta, wb = sb.alpha * Tb;
+        if (valid) *reinterpret_cast<float2*>(weights + base + i) = make_float2(wa, wb);
+        const float ar = sigmoidf_(rv[c].a.x), ag = sigmoidf_(rv[c].a.y), ab = sigmoidf_(rv[c].a.z);
+        const float br = sigmoidf_(rv[c].b.x), bg = sigmoidf_(rv[c].b.y), bb = sigmoidf_(rv[c].b.z);
+        const float fr = wa * ar + (last_b ? 0.f : wb * br);   // foreground sums exclude the background sample
+        const float fg = wa * ag + (last_b ? 0.f : wb * bg);
+        const float fb = wa * ab + (last_b ? 0.f : wb * bb);
+        v[5] += fr; v[6] += fg; v[7] += fb;
+        v[0] += last_b ? fr + wb * bcr : fr;
+        v[1] += last_b ? fg + wb * bcg : fg;
+        v[2] += last_b ? fb + wb * bcb : fb;
+        v[3] += wa * zv[c].x + wb * zv[c].y;
+        v[4] += wa + wb;
+    }
+    const float tot = reduce8(v, lane);                            // lane 4q holds quantity q
+    const float acc_t = __shfl_sync(0xffffffffu, tot, 16);
+    const float depth_t = __shfl_sync(0xffffffffu, tot, 12);
+    const int q = lane >> 2;
     if ((lane & 3) == 0) {
         if (q < 3) rgb[ray * 3 + q] = white_bkgd ? tot + (1.0f - acc_t) : tot;
         else if (q == 3) {
@@ -278,8 +384,18 @@ extern "C" int inerf_composite_fwd(const float* raw, const float* z, const float
     if (!raw || !z || !rays_d || !bc_rgb || !rgb || !disp || !acc || !depth || !weights)
         return fail(INERF_E_ARG, "inerf_composite_fwd: NULL pointer");
     if ((uintptr_t)raw & 15) return fail(INERF_E_ALIGN, "inerf_composite_fwd: raw must be 16-byte aligned");
-    int cc = pick_chunks(s);
     dim3 grid((n + 7) / 8), block(256);
+    const bool pairs = (s % 2 == 0) && s <= 512 && !(((uintptr_t)raw & 31) | ((uintptr_t)z & 7) | ((uintptr_t)weights & 7) |
+                                                      (noise ? (uintptr_t)noise & 7 : 0));
+    if (pairs) {
+        const int c2 = (s + 63) / 64;
+#define FWD2(C_) composite_fwd2_kernel<C_><<<grid, block, 0, as_stream(stream)>>>((const float4*)raw, z, rays_d, rays_d_stride, bc_rgb, \
+                                                                                 noise, n, s, white_bkgd, rgb, disp, acc, depth, weights, rgb_fg)
+        if (c2 <= 1) FWD2(1); else if (c2 == 2) FWD2(2); else if (c2 == 3) FWD2(3); else if (c2 == 4) FWD2(4); else FWD2(8);
+#undef FWD2
+        return check_launch("inerf_composite_fwd");
+    }
+    int cc = pick_chunks(s);
     DISPATCH_C(cc, (composite_fwd_kernel<C><<<grid, block, 0, as_stream(stream)>>>(
                        (const float4*)raw, z, rays_d, rays_d_stride, bc_rgb, noise, n, s, white_bkgd, rgb, disp, acc,
                        depth, weights, rgb_fg)));

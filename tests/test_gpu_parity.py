@@ -309,8 +309,16 @@ def test_render_rays_fp32_matches_reference(M, golden, tag):
             assert e <= 1e-5, f"{k}: {e:.3e}"
     # disp = 1/depth: compare depth-equivalent
     close(1.0 / r["disp_map"], 1.0 / torch.from_numpy(g[f"{tag}_disp_map"]), tol, "depth (1/disp)")
-    sub = st["sub"]
-    close(r["raw"][C(sub)], st[f"{tag}_raw1"], 5e-4, "fine raw (sigma is scaled ~x100 in the dense preset)")
+    sub = C(st["sub"])
+    if tag == "init":
+        close(r["raw"][sub], st[f"{tag}_raw1"], 5e-4, "fine raw")
+    # Dense preset: the fine depths inherit the ~1e-5 rounding floor above, gamma_10 multiplies it by 2^9 and
+    # alpha_linear by ~100, so raw is only comparable on IDENTICAL depths: the fine net on the reference's own z_vals.
+    with torch.no_grad():
+        raw1 = net.face_nerf_fine.query(rays[sub], C(st[f"{tag}_z1"]), aud, expr, lat)
+    ref1 = torch.from_numpy(st[f"{tag}_raw1"])
+    close(raw1[..., :3], ref1[..., :3], 5e-5, "fine rgb on the reference depths")
+    close(raw1[..., 3], ref1[..., 3], 5e-5 * max(1.0, float(ref1[..., 3].abs().max())), "fine sigma on the reference depths")
 
 
 def test_render_rays_perturb_pytest_draws(M, golden):
@@ -465,7 +473,7 @@ def test_bf16_rejects_small_s_and_embedded(M):
     net = head_net(M, O.init_face_nerf(7), "bf16")
     rays = b["rays"][:8].to(DEV)
     z = M.ops.sample_coarse(rays, 7)
-    with pytest.raises(RuntimeError, match="32 samples"):
+    with torch.no_grad(), pytest.raises(RuntimeError, match="32 samples"):
         net.query(rays, z, b["aud"].to(DEV), b["expr"].to(DEV), b["latent"].to(DEV))
 
 
