@@ -25,6 +25,7 @@
 // Weights are pre-packed (inerf_mlp_pack) as the exact shared-memory image of every stage: bf16,
 // K-major, 128-byte swizzle, in MMA issue order, so a stage is ONE contiguous bulk copy.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "mlp_common.cuh"
 #include "sm100_ptx.cuh"
@@ -88,11 +89,11 @@ static_assert(SMEM_ALLOC <= 232448, "shared memory budget");
 struct Bars {
     uint64_t wfull[NSTAGE], wempty[NSTAGE];
     uint64_t cbar[3];        // C0, C1, C2   (tcgen05.commit, once per layer)
-    uint64_t ebar[2];        // E0, E1       (256 epilogue threads, once per layer)
+    uint64_t ebar[2];        // E0, E1       (8 epilogue warps, once per layer)
     uint64_t pe_ready;       // 128 PE threads, once per iteration
     uint64_t pe_free;        // commit after the last MMA that reads the PE block
     uint64_t dirb_ready;     // 128 PE threads
-    uint64_t dirb_free;      // 256 epilogue threads
+    uint64_t dirb_free;      // 8 epilogue warps
     uint32_t tmem_base;
 };
 
@@ -168,9 +169,106 @@ __device__ __forceinline__ void epi_convert(const uint32_t (&r)[32], uint32_t* _
 }
 
 // ---------------------------------------------------------------------------------------------
+// compile-time layer geometry (must agree with build_schedule below, which lays out the packed blob)
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int lay_N(int l) { return l < 8 ? 256 : 128; }
+__host__ __device__ constexpr int lay_act_kb(int l) { return l == 0 ? 0 : (l <= 8 ? 4 : 2); }     // activation K-blocks (64 wide)
+__host__ __device__ constexpr bool lay_pe(int l) { return l == 0 || l == 5; }                     // + the gamma(p) K-block
+__host__ __device__ constexpr int lay_prev_N(int l) { return l == 0 ? 128 : lay_N(l - 1); }       // L0 follows V2 of the previous iteration
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// tcgen05.mma with the two smem descriptors given as (lo, hi) halves: lo = the 14-bit start-address field (+ LBO bit), advanced with
+// plain 32-bit adds of compile-time constants; hi is the same constant for every operand of this kernel.
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+struct IssueCtx {
+    Bars* bars;
+    uint32_t a_lo, pe_lo, w_lo, hi;      // descriptor halves of the activation / PE / weight-ring bases
+    uint32_t tmem_base;
+    uint32_t stage, wpar;                // weight ring position and the parity of its current round
+    uint32_t layer_ctr, iter_ctr;
+    long long t_e, t_w, t_pe;            // trace build: where the issuer waits
+};
+
+// All MMAs of layer L for both 128-row slots, straight-line: every descriptor offset, wait and commit below is a compile-time
+// constant of (L, half, K-block), so a step costs ~10 uniform-datapath instructions per tcgen05.mma instead of a table decode.
+// (The table-driven form was issue-latency bound: ~150 dependent SASS instructions per 8-MMA step on ONE thread, ~1000 cycles
+// against the 512 the tensor pipe needs -- profiles/r01_mlp_ablation.txt.)
+template <int L, bool TRACE, int ABL>
+__device__ __forceinline__ void issue_layer(IssueCtx& c) {
+    constexpr int N = lay_N(L), NH = N / 2, NKB = lay_act_kb(L), CNT = NKB + (lay_pe(L) ? 1 : 0);
+    constexpr int KB_PER_HALF_PREV = lay_prev_N(L) / 128;     // activation K-blocks written by ONE half of the previous epilogue
+    constexpr int N_OUT_H0 = NH / 64;                          // K-blocks epi(h0) of THIS layer overwrites
+    constexpr int N_FIRST = NKB < N_OUT_H0 ? NKB : N_OUT_H0;   // leading K-blocks of h1 that epi(h0) will overwrite
+    constexpr uint32_t IDESC = umma_idesc_bf16(128, NH);
+    Bars* bars = c.bars;
+    const uint32_t par_prev = (c.layer_ctr - 1) & 1;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int i = 0; i < CNT; ++i) {
+            const bool is_pe = (i == NKB);                     // the PE block comes last in both halves
+            long long c0 = 0;
+            if constexpr (TRACE) c0 = clock64();
+            if (h == 0 && c.layer_ctr > 0) {                   // each epilogue event is waited ONCE per layer, at its first use
+                if (L == 0) {                                  // new iteration: both accumulator halves of V2 drained
+                    if (i == 0) { wait_or_report<TRACE>(&bars->ebar[0], par_prev, 201, L, (int)c.layer_ctr);
+                                  wait_or_report<TRACE>(&bars->ebar[1], par_prev, 202, L, (int)c.layer_ctr); }
+                } else if (!is_pe) {
+                    if (i == 0) wait_or_report<TRACE>(&bars->ebar[0], par_prev, 201, L, (int)c.layer_ctr);
+                    if (i == KB_PER_HALF_PREV) wait_or_report<TRACE>(&bars->ebar[1], par_prev, 202, L, (int)c.layer_ctr);
+                }
+            }
+            if constexpr (TRACE) { const long long c1 = clock64(); c.t_e += c1 - c0; c0 = c1; }
+            if (L == 0 && h == 0 && i == 0) wait_or_report<TRACE>(&bars->pe_ready, c.iter_ctr & 1, 203, L, (int)c.iter_ctr);
+            if constexpr (TRACE) { const long long c1 = clock64(); c.t_pe += c1 - c0; c0 = c1; }
+            if (!(ABL & 2) || (c.layer_ctr == 0 && L == 0 && h * CNT + i < NSTAGE))
+                wait_or_report<TRACE>(&bars->wfull[c.stage], c.wpar, 204, L, (int)c.stage);
+            if constexpr (TRACE) c.t_w += clock64() - c0;
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t b_lo = c.w_lo + c.stage * (STAGE_BYTES >> 4);
+#pragma unroll
+                for (int slot = 0; slot < 2; ++slot) {
+                    const uint32_t a_lo = is_pe ? c.pe_lo + slot * (16384 >> 4) : c.a_lo + slot * (65536 >> 4) + i * (16384 >> 4);
+                    const uint32_t d = c.tmem_base + slot * 256 + h * NH;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, a_lo + 2 * k, b_lo + 2 * k, c.hi, IDESC, (i == 0 && k == 0) ? 0u : 1u);
+                }
+                umma_commit(&bars->wempty[c.stage]);
+                const bool last = (i == CNT - 1);
+                if (h == 0 && last) umma_commit(&bars->cbar[0]);
+                if (h == 1 && (N_FIRST > 0 ? i == N_FIRST - 1 : last)) umma_commit(&bars->cbar[1]);
+                if (h == 1 && last) umma_commit(&bars->cbar[2]);
+                if (h == 1 && last && L == 5) umma_commit(&bars->pe_free);
+            }
+            __syncwarp();
+            if (++c.stage == NSTAGE) { c.stage = 0; c.wpar ^= 1; }
+        }
+    }
+    ++c.layer_ctr;
+}
+
+// ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <bool TRACE>
+// ABL (builds with -DINERF_ABLATION only; profiles/ablate_mlp.py): bit 0 = epilogue keeps its barrier protocol but skips the
+// TMEM loads / conversion / smem stores, bit 1 = weights are loaded once (no streaming, no full-barrier waits), bit 2 = the
+// positional-encoding warps skip sincosf.  Outputs are garbage; only the timing is meaningful.
+template <bool TRACE, int ABL = 0>
 __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, int n_steps, int n_rays, float* __restrict__ trace) {
     // Dynamic shared memory is the only shared allocation of this kernel, so it starts at offset 0 of the CTA's
     // window: 1024-byte aligned as the 128B-swizzle atoms need.  (No pointer re-alignment arithmetic here: it would
@@ -193,11 +291,11 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars->wfull[s], 1); mbar_init(&bars->wempty[s], 1); }
         for (int j = 0; j < 3; ++j) mbar_init(&bars->cbar[j], 1);
-        for (int j = 0; j < 2; ++j) mbar_init(&bars->ebar[j], N_EPI);
+        for (int j = 0; j < 2; ++j) mbar_init(&bars->ebar[j], N_EPI / 32);
         mbar_init(&bars->pe_ready, N_PE);
         mbar_init(&bars->pe_free, 1);
         mbar_init(&bars->dirb_ready, N_PE);
-        mbar_init(&bars->dirb_free, N_EPI);
+        mbar_init(&bars->dirb_free, N_EPI / 32);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -217,6 +315,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
             for (long long it = blockIdx.x; it < n_iter; it += gridDim.x) {
                 for (int s = 0; s < n_steps; ++s, ++g) {
                     const uint32_t stage = g % NSTAGE, round = g / NSTAGE;
+                    if ((ABL & 2) && g >= NSTAGE) continue;
                     wait_or_report<TRACE>(&bars->wempty[stage], (round & 1) ^ 1, 101, s, (int)g);
                     const uint32_t bytes = (uint32_t)c_steps[s].n8 * 8u * 128u;
                     mbar_arrive_expect_tx(&bars->wfull[stage], bytes);
@@ -225,59 +324,26 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer ========================================================
-        if (lane == 0) {
-            uint32_t g = 0, layer_ctr = 0, iter_ctr = 0;
-            long long t_e = 0, t_w = 0, t_pe = 0, t_tot = clock64();      // trace build: where the issuer waits
-            const uint32_t act_base = smem_u32(sm + OFF_ACT), pe_base = smem_u32(sm + OFF_PE), w_base = smem_u32(sm + OFF_W);
-            for (long long it = blockIdx.x; it < n_iter; it += gridDim.x, ++iter_ctr) {
-                int cur_layer = 0;
-                uint32_t waited = 0;
-                for (int s = 0; s < n_steps; ++s, ++g) {
-                    const Step st = c_steps[s];
-                    if (st.layer != cur_layer) { cur_layer = st.layer; ++layer_ctr; waited = 0; }
-                    // Events produced by the epilogue of the previous layer (global layer counter - 1).  Each event is
-                    // waited at most ONCE per layer: a parity wait repeated after this layer's own C1/C2 commits could
-                    // observe the barrier two phases ahead (the epilogue of THIS layer may already have arrived) and
-                    // block forever.
-                    const uint32_t need = st.wait & ~waited;
-                    waited |= need;
-                    long long c0 = 0;
-                    if constexpr (TRACE) c0 = clock64();
-                    if ((need & (W_E0 | W_E1)) && layer_ctr > 0) {
-                        const uint32_t par = (layer_ctr - 1) & 1;
-                        if (need & W_E0) wait_or_report<TRACE>(&bars->ebar[0], par, 201, s, (int)layer_ctr);
-                        if (need & W_E1) wait_or_report<TRACE>(&bars->ebar[1], par, 202, s, (int)layer_ctr);
-                    }
-                    if constexpr (TRACE) { const long long c1 = clock64(); t_e += c1 - c0; c0 = c1; }
-                    if (need & W_PE) wait_or_report<TRACE>(&bars->pe_ready, iter_ctr & 1, 203, s, (int)iter_ctr);
-                    if constexpr (TRACE) { const long long c1 = clock64(); t_pe += c1 - c0; c0 = c1; }
-                    const uint32_t stage = g % NSTAGE, round = g / NSTAGE;
-                    wait_or_report<TRACE>(&bars->wfull[stage], round & 1, 204, s, (int)g);
-                    if constexpr (TRACE) t_w += clock64() - c0;
-                    tc_fence_after();
-                    const uint32_t idesc = umma_idesc_bf16(128, st.n8 * 8);
-                    const uint64_t bd = umma_desc_sw128(w_base + stage * STAGE_BYTES);
-#pragma unroll
-                    for (int slot = 0; slot < 2; ++slot) {
-                        const uint32_t a_addr = (st.a_kb < 4) ? act_base + slot * 65536 + st.a_kb * 16384 : pe_base + slot * 16384;
-                        const uint64_t ad = umma_desc_sw128(a_addr);
-                        const uint32_t d = tmem_base + slot * 256 + st.acc_col;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (st.first && k == 0) ? 0u : 1u);
-                    }
-                    umma_commit(&bars->wempty[stage]);
-                    if (st.commit & C_C0) umma_commit(&bars->cbar[0]);
-                    if (st.commit & C_C1) umma_commit(&bars->cbar[1]);
-                    if (st.commit & C_C2) umma_commit(&bars->cbar[2]);
-                    if (st.commit & C_PEFREE) umma_commit(&bars->pe_free);
-                }
-                ++layer_ctr;      // the next iteration's L0 is a new layer
-            }
-            if constexpr (TRACE) {      // per-CTA issuer timing after the activation trace: {total, wait E, wait PE, wait weights, iterations}
+        // ================= MMA issuer (whole warp converged; one elected lane issues) ==========
+        IssueCtx c;
+        c.bars = bars;
+        c.hi = (uint32_t)(umma_desc_sw128(0) >> 32);
+        c.a_lo = (uint32_t)umma_desc_sw128(smem_u32(sm + OFF_ACT));
+        c.pe_lo = (uint32_t)umma_desc_sw128(smem_u32(sm + OFF_PE));
+        c.w_lo = (uint32_t)umma_desc_sw128(smem_u32(sm + OFF_W));
+        c.tmem_base = tmem_base;
+        c.stage = 0; c.wpar = 0; c.layer_ctr = 0; c.iter_ctr = 0;
+        c.t_e = c.t_w = c.t_pe = 0;
+        const long long t_tot = clock64();
+        for (long long it = blockIdx.x; it < n_iter; it += gridDim.x, ++c.iter_ctr) {
+            issue_layer<0, TRACE, ABL>(c); issue_layer<1, TRACE, ABL>(c); issue_layer<2, TRACE, ABL>(c); issue_layer<3, TRACE, ABL>(c);
+            issue_layer<4, TRACE, ABL>(c); issue_layer<5, TRACE, ABL>(c); issue_layer<6, TRACE, ABL>(c); issue_layer<7, TRACE, ABL>(c);
+            issue_layer<8, TRACE, ABL>(c); issue_layer<9, TRACE, ABL>(c); issue_layer<10, TRACE, ABL>(c);
+        }
+        if constexpr (TRACE) {      // per-CTA issuer timing after the activation trace: {total, wait E, wait PE, wait weights, iterations}
+            if (lane == 0) {
                 float* t = trace + (size_t)11 * 256 * 256 + blockIdx.x * 8;
-                t[0] = (float)(clock64() - t_tot); t[1] = (float)t_e; t[2] = (float)t_pe; t[3] = (float)t_w; t[4] = (float)iter_ctr;
+                t[0] = (float)(clock64() - t_tot); t[1] = (float)c.t_e; t[2] = (float)c.t_pe; t[3] = (float)c.t_w; t[4] = (float)c.iter_ctr;
             }
         }
     } else if (warp >= 4 && warp < 12) {
@@ -310,7 +376,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                     const int nchunk = NH >> 5;      // 4 (N=256) or 2 (N=128)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        if (c < nchunk) {
+                        if (c < nchunk && !(ABL & 1)) {
                             uint32_t r[32];
                             tmem_ld32(t_lane + h * NH + c * 32, r);
                             tmem_wait_ld();
@@ -332,7 +398,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                         __syncwarp();      // h1 has finished reading the K-blocks written below
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
-                            if (c < nchunk) {
+                            if (c < nchunk && !(ABL & 1)) {
                                 const int f0 = h * NH + c * 32;
                                 uint8_t* kb = act + (f0 >> 6) * 16384 + row_off;
                                 const int ch0 = (f0 & 63) >> 3;                // first 16-byte chunk inside the 128-byte row
@@ -346,9 +412,15 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                         }
                         fence_proxy_async_smem();
                     }
-                    mbar_arrive(&bars->ebar[h]);
+                    // one arrival per warp: 256 per-thread arrivals on one mbarrier serialise in the shared-memory pipe and sit on
+                    // the layer-to-layer critical path (E1 gates the next layer's third K-block)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->ebar[h]);
                 }
-                if (l == 8) mbar_arrive(&bars->dirb_free);
+                if (l == 8) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->dirb_free);
+                }
             }
             if (in_range) {
                 float4 o;
@@ -387,7 +459,8 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         float sn, cs;
-                        sincosf(v[c] * (float)(1 << f), &sn, &cs);
+                        if constexpr (ABL & 4) { sn = v[c]; cs = zz; }
+                        else sincosf(v[c] * (float)(1 << f), &sn, &cs);
                         v[3 + 6 * f + c] = sn;
                         v[6 + 6 * f + c] = cs;
                     }
@@ -603,6 +676,16 @@ int mlp_bf16_launch(const MlpArgs& a, bool embedded, cudaStream_t st) {
         }
         if (g_hang_host) for (int i = 0; i < 8; ++i) g_hang_host[i] = 0;
     }
+#ifdef INERF_ABLATION
+    if (const char* e = getenv("INERF_ABL")) {
+        const int abl = atoi(e);
+#define ABL_CASE(N_) case N_: cudaFuncSetAttribute(mlp_bf16_kernel<false, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC); \
+                              mlp_bf16_kernel<false, N_><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, nullptr); break;
+        switch (abl) { ABL_CASE(1) ABL_CASE(2) ABL_CASE(3) ABL_CASE(4) ABL_CASE(5) ABL_CASE(6) ABL_CASE(7) default: break; }
+#undef ABL_CASE
+        if (abl >= 1 && abl <= 7) return check_launch("inerf_mlp_fwd[bf16,ablation]");
+    }
+#endif
     if (a.trace) mlp_bf16_kernel<true><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, a.trace);
     else mlp_bf16_kernel<false><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, nullptr);
     return check_launch("inerf_mlp_fwd[bf16]");

@@ -108,6 +108,7 @@ struct Args {
     float* d;               // correctness: [128*CG][N]
     float* report;          // per CTA: {cycles, n_mma, epilogue loops}
     int N, slots, iters, interfere, check;
+    int mimic;              // 0: back-to-back MMAs; 1: + a tcgen05.commit per 8-MMA step (nobody waits); 2: + half/layer commits answered by a responder warp
 };
 
 // smem map: A [2 slots][4 kb][16 KB] = 128 KB | B [4 kb][up to 32 KB]... B only one K-block image is kept resident per kb: 4 x N*128
@@ -122,6 +123,9 @@ __global__ void __launch_bounds__(384, 1) rate_kernel(Args p) {
     uint64_t& bar_load = *reinterpret_cast<uint64_t*>(sm + OFF_SCR + 16384 + 8);
     uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(sm + OFF_SCR + 16384 + 16);
     volatile int& stop_flag = *reinterpret_cast<volatile int*>(sm + OFF_SCR + 16384 + 20);
+    uint64_t* ring = reinterpret_cast<uint64_t*>(sm + OFF_SCR + 16384 + 32);     // [3] per-step commits, nobody waits
+    uint64_t* cbar = ring + 3;                                                   // [2] C0, C2
+    uint64_t* ebar = ring + 5;                                                   // [2] E0, E1 (8 responder warps)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
     const int NB = p.N / CG;                       // B rows held by this CTA
@@ -132,6 +136,9 @@ __global__ void __launch_bounds__(384, 1) rate_kernel(Args p) {
     if (threadIdx.x == 0) {
         mbar_init(&bar_done, 1);
         mbar_init(&bar_load, 1);
+        for (int j = 0; j < 5; ++j) mbar_init(&ring[j], 1);
+        mbar_init(&ebar[0], 8);
+        mbar_init(&ebar[1], 8);
         fence_mbar_init();
         stop_flag = 0;
     }
@@ -180,6 +187,30 @@ __global__ void __launch_bounds__(384, 1) rate_kernel(Args p) {
         const uint32_t a_base = smem_u32(sm + OFF_A), b_base = smem_u32(sm + off_b);
         const long long t0 = clock64();
         long long n_mma = 0;
+        if (p.mimic) {
+            // the issue pattern of mlp_bf16_kernel: layers of two output halves (N = 128 each, D = slot*256 + h*128), 4 K-blocks per
+            // half, both slots per K-block, a commit per step (weight stage release), C0 / C2 commits per half, and (mimic >= 2) the
+            // E0 / E1 waits answered by the responder warps below
+            const uint32_t idh = umma_idesc_bf16(128, 128);
+            uint32_t g = 0, lc = 0;
+            for (int it = 0; it < p.iters; ++it, ++lc)
+                for (int h = 0; h < 2; ++h)
+                    for (int kb = 0; kb < 4; ++kb, ++g) {
+                        if (p.mimic >= 2 && lc > 0 && h == 0 && (kb == 0 || kb == 2)) bounded_wait(&ebar[kb >> 1], (lc - 1) & 1);
+                        const uint64_t bd = umma_desc_sw128(b_base + kb * 16384);
+                        for (int slot = 0; slot < 2; ++slot) {
+                            const uint32_t d = tmem_base + slot * 256 + h * 128;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t a = umma_desc_sw128(a_base + slot * 65536 + kb * 16384) + 2 * k;
+                                mma<CG, false>(d, a, bd + 2 * k, idh, (kb | k) ? 1u : 0u);
+                                ++n_mma;
+                            }
+                        }
+                        commit<CG>(&ring[g % 3]);
+                        if (kb == 3) commit<CG>(&cbar[h]);
+                    }
+        } else
         for (int it = 0; it < p.iters; ++it)
             for (int kb = 0; kb < 4; ++kb) {
                 const uint64_t bd = umma_desc_sw128(b_base + (alias_b ? (kb & 1) : kb) * b_img_bytes);
@@ -201,6 +232,39 @@ __global__ void __launch_bounds__(384, 1) rate_kernel(Args p) {
         p.report[blockIdx.x * 4 + 0] = (float)(t1 - t0);
         p.report[blockIdx.x * 4 + 1] = (float)n_mma;
         stop_flag = 1;
+    } else if (warp >= 4 && warp < 12 && p.mimic >= 2) {
+        // responder = the epilogue's barrier protocol (optionally with its TMEM-load / st.shared work: interfere = 1)
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 3) * 256;
+        uint8_t* scr = sm + OFF_SCR + (row >> 3) * 1024 + (row & 7) * 128;
+        uint32_t sink = 0;
+        for (int lc = 0; lc < p.iters; ++lc)
+            for (int h = 0; h < 2; ++h) {
+                bounded_wait(&cbar[h], lc & 1);
+                __syncwarp();
+                tc_fence_after();
+                if (p.interfere) {
+                    uint32_t packed[64];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t r[32];
+                        tmem_ld32(t_lane + h * 128 + c * 32, r);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) packed[c * 16 + j] = pack_bf16x2_relu(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                    }
+                    tc_fence_before();
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)
+                        *reinterpret_cast<uint4*>(scr + (((q & 7) ^ (row & 7)) << 4)) =
+                            make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                    fence_proxy_async_smem();
+                    sink += packed[3];
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ebar[h]);
+            }
+        if (sink == 0x12345u) p.report[blockIdx.x * 4 + 3] = 1.f;
     } else if (warp >= 4 && warp < 12 && p.interfere) {
         // epilogue-like traffic: tcgen05.ld of 128 fp32 columns per row + 16 x 16-byte swizzled st.shared (interfere = 1)
         // or + tcgen05.st of 64 packed columns (interfere = 2)
@@ -229,8 +293,9 @@ __global__ void __launch_bounds__(384, 1) rate_kernel(Args p) {
                 uint32_t a[32], b[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { a[j] = packed[j]; b[j] = packed[32 + j]; }
-                tmem_st32(t_lane + 448, a);          // columns never read by the MMAs of this probe
-                tmem_st32(t_lane + 480, b);
+                const uint32_t t_st = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+                tmem_st32(t_st + 448, a);            // columns never read by the ts-mode MMAs of this probe
+                tmem_st32(t_st + 480, b);
                 tmem_wait_st();
             }
             sink += packed[5];
@@ -238,7 +303,10 @@ __global__ void __launch_bounds__(384, 1) rate_kernel(Args p) {
         }
         if (lane == 0 && warp == 4) p.report[blockIdx.x * 4 + 2] = (float)loops + (sink == 0x12345u ? 1.f : 0.f);
     }
-    if (CG == 2 && rank == 1 && threadIdx.x == 0) bounded_wait(&bar_done, 0);      // multicast commit reaches the peer too
+    if (CG == 2 && rank == 1 && threadIdx.x == 0) {       // the multicast commit reaches the peer too: release its epilogue warps
+        bounded_wait(&bar_done, 0);
+        stop_flag = 1;
+    }
     __syncthreads();
 
     // ---- correctness read-back ---------------------------------------------------------------------------------------
@@ -318,7 +386,7 @@ int check_case(int N) {
     cudaMemcpy(da, ai.data(), ai.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(db, bi.data(), bi.size(), cudaMemcpyHostToDevice);
     cudaMemset(dd, 0xff, D.size() * 4);
-    Args a{da, db, dd, rep, N, 1, 1, 0, 1};
+    Args a{da, db, dd, rep, N, 1, 1, 0, 1, 0};
     int rc = launch<CG, TS>(a, CG);
     long bad = 0;
     if (!rc) {
@@ -334,11 +402,11 @@ int check_case(int N) {
 }
 
 template <int CG, bool TS>
-void rate_case(int N, int slots, int interfere, int grid) {
+void rate_case(int N, int slots, int interfere, int grid, int mimic = 0) {
     float* rep;
     cudaMalloc(&rep, 4096 * 4);
     cudaMemset(rep, 0, 4096 * 4);
-    Args a{nullptr, nullptr, nullptr, rep, N, slots, 200, interfere, 0};
+    Args a{nullptr, nullptr, nullptr, rep, N, slots, 200, interfere, 0, mimic};
     if (launch<CG, TS>(a, grid)) { cudaFree(rep); return; }
     std::vector<float> h(4096);
     cudaMemcpy(h.data(), rep, 4096 * 4, cudaMemcpyDeviceToHost);
@@ -346,6 +414,7 @@ void rate_case(int N, int slots, int interfere, int grid) {
     for (int b = 0; b < grid; b += CG) { cyc += h[b * 4]; nm += h[b * 4 + 1]; loops += h[b * 4 + 2]; ++cnt; }
     cyc /= cnt; nm /= cnt; loops /= cnt;
     const double mac = 128.0 * CG * N * 16, per = cyc / nm;
+    if (mimic) printf("mimic=%d ", mimic);
     printf("rate %s cg%d N=%3d slots=%d interfere=%d grid=%3d: %7.1f cyc/MMA  -> %6.0f MAC/clk/SM (%.0f%% of 4096)   epilogue: %.0f rows-of-128col per kcyc per CTA\n",
            TS ? "ts" : "ss", CG, N, slots, interfere, grid, per, mac / per / CG, 100.0 * mac / per / CG / 4096.0,
            loops * 256.0 / (cyc / 1000.0));
@@ -365,16 +434,19 @@ int main(int argc, char** argv) {
     fails += check_case<2, false>(128);
     const int G = 148;
     for (int inter = 0; inter <= 2; ++inter) {
-        rate_case<1, false>(128, 2, inter, G);
-        rate_case<1, false>(256, 2, inter, G);
+        if (inter < 2) {
+            rate_case<1, false>(128, 2, inter, G);
+            rate_case<1, false>(256, 2, inter, G);
+            rate_case<2, false>(256, 2, inter, G);
+            rate_case<2, false>(128, 2, inter, G);
+        }
         rate_case<1, true>(128, 1, inter, G);
         rate_case<1, true>(256, 1, inter, G);
-        rate_case<2, false>(256, 2, inter, G);
-        rate_case<2, false>(128, 2, inter, G);
         rate_case<2, true>(256, 1, inter, G);
     }
-    rate_case<1, false>(128, 2, 1, 1);
-    rate_case<2, false>(256, 2, 1, 2);
+    rate_case<1, false>(128, 2, 0, G, 1);
+    rate_case<1, false>(128, 2, 0, G, 2);
+    rate_case<1, false>(128, 2, 1, G, 2);
     printf(fails ? "UMMA RATE: %d check(s) FAILED\n" : "UMMA RATE: all checks passed\n", fails);
     return 0;
 }
