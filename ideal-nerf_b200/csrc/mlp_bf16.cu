@@ -38,7 +38,7 @@ namespace {
 constexpr int NSTAGE = 3;
 constexpr int STAGE_BYTES = 16384;
 constexpr int MAX_STEPS = 80;
-constexpr int RMAX = 5;            // rays a 128-row slot can touch (s >= 32)
+constexpr int RMAX = 4;            // rays a 128-row slot can touch (s >= 43)
 constexpr int NTHREADS_BF16 = 512;
 constexpr int N_EPI = 256, N_PE = 128;
 
@@ -77,11 +77,14 @@ __constant__ Step c_steps[MAX_STEPS];
 constexpr int OFF_ACT = 0;                               // [2][4][16384]
 constexpr int OFF_PE = 131072;                           // [2][16384]
 constexpr int OFF_W = 163840;                            // [NSTAGE][16384]
-constexpr int OFF_BIAS = OFF_W + NSTAGE * STAGE_BYTES;   // 2436 floats (CondLayout)
-constexpr int OFF_AW = OFF_BIAS + 9744;                  // alpha_linear.weight 256 floats
+constexpr int OFF_ONES = OFF_W + NSTAGE * STAGE_BYTES;   // A operand of the bias MMAs: 128 x 16 bf16 ones, no-swizzle core-matrix layout
+constexpr int OFF_BT = OFF_ONES + 4096;                  // [2][4096] bias tiles (B operand of the bias MMAs), streamed per layer half
+constexpr int OFF_SB = OFF_BT + 2 * 4096;                // alpha_linear.bias, rgb_linear.bias (4 floats)
+constexpr int OFF_AW = OFF_SB + 16;                      // alpha_linear.weight 256 floats
 constexpr int OFF_RW = OFF_AW + 1024;                    // rgb_linear.weight 3x128 floats
 constexpr int OFF_DIRB = OFF_RW + 1536;                  // [2][RMAX][128] floats
 constexpr int OFF_BAR = OFF_DIRB + 2 * RMAX * 128 * 4;   // mbarriers
+constexpr int BIAS_TILE_BYTES_TOTAL = 16 * 4096 + 6 * 2048;   // per call, after the 2436 folded fp32 biases of `cond`
 constexpr int SMEM_BYTES = OFF_BAR + 256;
 constexpr int SMEM_ALLOC = SMEM_BYTES;
 static_assert(SMEM_ALLOC <= 232448, "shared memory budget");
@@ -94,6 +97,7 @@ struct Bars {
     uint64_t pe_free;        // commit after the last MMA that reads the PE block
     uint64_t dirb_ready;     // 128 PE threads
     uint64_t dirb_free;      // 8 epilogue warps
+    uint64_t bfull[2], bempty[2];   // bias-tile ring
     uint32_t tmem_base;
 };
 
@@ -134,14 +138,12 @@ __device__ __forceinline__ LayerInfo layer_info(int l) {
 // One 32-column chunk of an epilogue: +bias (+per-ray view bias), ReLU, bf16 pack; KIND 1 also accumulates
 // alpha_linear, KIND 3 rgb_linear, in fp32 from the un-rounded activations.
 template <int KIND, bool TRACE>
-__device__ __forceinline__ void epi_convert(const uint32_t (&r)[32], uint32_t* __restrict__ packed16, const float* __restrict__ bsrc,
+__device__ __forceinline__ void epi_convert(const uint32_t (&r)[32], uint32_t* __restrict__ packed16,
                                             const float* __restrict__ dsrc, const float* __restrict__ aw, const float* __restrict__ rw,
                                             float& alpha, float& rgb0, float& rgb1, float& rgb2, float* tr, bool dump) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-        const float4 b = *reinterpret_cast<const float4*>(bsrc + j);
-        float v[4] = {__uint_as_float(r[j]) + b.x, __uint_as_float(r[j + 1]) + b.y, __uint_as_float(r[j + 2]) + b.z,
-                      __uint_as_float(r[j + 3]) + b.w};
+        float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])};
         if constexpr (KIND == 2) {
             const float4 d = *reinterpret_cast<const float4*>(dsrc + j);
             v[0] += d.x; v[1] += d.y; v[2] += d.z; v[3] += d.w;
@@ -194,11 +196,17 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, u
         : "memory");
 }
 
+// Descriptor halves of a K-major, NON-swizzled 16-column (K = 16) bf16 tile stored as [row/8][k/8][row%8][k%8]: 8x8 core matrices of
+// 128 contiguous bytes, the two K halves 128 B apart (leading byte offset), 8-row groups 256 B apart (stride byte offset).
+constexpr uint32_t HI_NOSWZ = (256u >> 4) | (1u << 14);
+__device__ __forceinline__ uint32_t desc_lo_noswz(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | ((128u >> 4) << 16); }
+
 struct IssueCtx {
     Bars* bars;
     uint32_t a_lo, pe_lo, w_lo, hi;      // descriptor halves of the activation / PE / weight-ring bases
     uint32_t tmem_base;
     uint32_t stage, wpar;                // weight ring position and the parity of its current round
+    uint32_t ones_lo, bt_lo, bslot, bpar;   // bias MMA operands (no-swizzle descriptors) and the bias ring position
     uint32_t layer_ctr, iter_ctr;
     long long t_e, t_w, t_pe;            // trace build: where the issuer waits
 };
@@ -238,15 +246,24 @@ __device__ __forceinline__ void issue_layer(IssueCtx& c) {
             if (!(ABL & 2) || (c.layer_ctr == 0 && L == 0 && h * CNT + i < NSTAGE))
                 wait_or_report<TRACE>(&bars->wfull[c.stage], c.wpar, 204, L, (int)c.stage);
             if constexpr (TRACE) c.t_w += clock64() - c0;
+            if (i == 0) wait_or_report<TRACE>(&bars->bfull[c.bslot], c.bpar, 205, L, (int)c.bslot);
             tc_fence_after();
             if (elect_one()) {
+                if (i == 0) {
+                    // bias: D = ones[128x16] . tile[NHx16]^T with tile columns (hi, lo, 0, ...) = the folded bias split in two bf16;
+                    // this MMA overwrites the accumulator, every weight MMA below accumulates
+#pragma unroll
+                    for (int slot = 0; slot < 2; ++slot)
+                        umma_bf16_lohi(c.tmem_base + slot * 256 + h * NH, c.ones_lo, c.bt_lo + c.bslot * (4096 >> 4), HI_NOSWZ, IDESC, 0u);
+                    umma_commit(&bars->bempty[c.bslot]);
+                }
                 const uint32_t b_lo = c.w_lo + c.stage * (STAGE_BYTES >> 4);
 #pragma unroll
                 for (int slot = 0; slot < 2; ++slot) {
                     const uint32_t a_lo = is_pe ? c.pe_lo + slot * (16384 >> 4) : c.a_lo + slot * (65536 >> 4) + i * (16384 >> 4);
                     const uint32_t d = c.tmem_base + slot * 256 + h * NH;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, a_lo + 2 * k, b_lo + 2 * k, c.hi, IDESC, (i == 0 && k == 0) ? 0u : 1u);
+                    for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, a_lo + 2 * k, b_lo + 2 * k, c.hi, IDESC, 1u);
                 }
                 umma_commit(&bars->wempty[c.stage]);
                 const bool last = (i == CNT - 1);
@@ -256,6 +273,7 @@ __device__ __forceinline__ void issue_layer(IssueCtx& c) {
                 if (h == 1 && last && L == 5) umma_commit(&bars->pe_free);
             }
             __syncwarp();
+            if (i == 0) { c.bslot ^= 1; if (c.bslot == 0) c.bpar ^= 1; }
             if (++c.stage == NSTAGE) { c.stage = 0; c.wpar ^= 1; }
         }
     }
@@ -267,7 +285,7 @@ __device__ __forceinline__ void issue_layer(IssueCtx& c) {
 // ---------------------------------------------------------------------------------------------
 // ABL (builds with -DINERF_ABLATION only; profiles/ablate_mlp.py): bit 0 = epilogue keeps its barrier protocol but skips the
 // TMEM loads / conversion / smem stores, bit 1 = weights are loaded once (no streaming, no full-barrier waits), bit 2 = the
-// positional-encoding warps skip sincosf.  Outputs are garbage; only the timing is meaningful.
+// positional-encoding warps skip sincosf, bit 3 = the epilogue skips only its TMEM loads, bit 4 = only its bias/ReLU/convert math.  Outputs are garbage; only the timing is meaningful.
 template <bool TRACE, int ABL = 0>
 __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, int n_steps, int n_rays, float* __restrict__ trace) {
     // Dynamic shared memory is the only shared allocation of this kernel, so it starts at offset 0 of the CTA's
@@ -276,7 +294,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
     extern __shared__ __align__(1024) uint8_t sm[];
     if ((smem_u32(sm) & 1023u) != 0) __trap();
     Bars* bars = reinterpret_cast<Bars*>(sm + OFF_BAR);
-    float* s_bias = reinterpret_cast<float*>(sm + OFF_BIAS);
+    float* s_sb = reinterpret_cast<float*>(sm + OFF_SB);
     float* s_aw = reinterpret_cast<float*>(sm + OFF_AW);
     float* s_rw = reinterpret_cast<float*>(sm + OFF_RW);
     float* s_dirb = reinterpret_cast<float*>(sm + OFF_DIRB);
@@ -285,7 +303,10 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
     const long long n_iter = (a.P + 255) / 256;
 
     // ---- one-time setup -------------------------------------------------------------------
-    for (int i = tid; i < 2436; i += NTHREADS_BF16) s_bias[i] = a.cond[i];
+    if (tid < 4) s_sb[tid] = a.cond[8 * 256 + 3 * 128 + tid];
+    for (int i = tid; i < 256; i += NTHREADS_BF16)           // the ones tile (bf16 1.0 = 0x3F80), read by the async proxy
+        reinterpret_cast<uint4*>(sm + OFF_ONES)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
     for (int i = tid; i < 256; i += NTHREADS_BF16) s_aw[i] = a.w[P_ALPHA_W][i];
     for (int i = tid; i < 384; i += NTHREADS_BF16) s_rw[i] = a.w[P_RGB_W][i];
     if (tid == 0) {
@@ -296,6 +317,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
         mbar_init(&bars->pe_free, 1);
         mbar_init(&bars->dirb_ready, N_PE);
         mbar_init(&bars->dirb_free, N_EPI / 32);
+        for (int j = 0; j < 2; ++j) { mbar_init(&bars->bfull[j], 1); mbar_init(&bars->bempty[j], 1); }
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -311,10 +333,20 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
         // ================= weight producer ==================================================
         if (lane == 0) {
             const uint8_t* blob = reinterpret_cast<const uint8_t*>(a.packed);
-            uint32_t g = 0;
+            const uint8_t* tiles = reinterpret_cast<const uint8_t*>(a.cond + 2436);
+            uint32_t g = 0, bh = 0;
             for (long long it = blockIdx.x; it < n_iter; it += gridDim.x) {
                 for (int s = 0; s < n_steps; ++s, ++g) {
                     const uint32_t stage = g % NSTAGE, round = g / NSTAGE;
+                    if (c_steps[s].first) {            // first step of a (layer, half): its bias tile
+                        const uint32_t slot = bh & 1, l = c_steps[s].layer, h = c_steps[s].acc_col ? 1u : 0u;
+                        const uint32_t bytes = (uint32_t)c_steps[s].n8 * 8u * 32u;
+                        const uint32_t off = l < 8 ? (2 * l + h) * 4096u : 65536u + (2 * (l - 8) + h) * 2048u;
+                        wait_or_report<TRACE>(&bars->bempty[slot], ((bh >> 1) & 1) ^ 1, 102, s, (int)bh);
+                        mbar_arrive_expect_tx(&bars->bfull[slot], bytes);
+                        bulk_g2s(sm + OFF_BT + slot * 4096, tiles + off, bytes, &bars->bfull[slot]);
+                        ++bh;
+                    }
                     if ((ABL & 2) && g >= NSTAGE) continue;
                     wait_or_report<TRACE>(&bars->wempty[stage], (round & 1) ^ 1, 101, s, (int)g);
                     const uint32_t bytes = (uint32_t)c_steps[s].n8 * 8u * 128u;
@@ -332,6 +364,9 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
         c.pe_lo = (uint32_t)umma_desc_sw128(smem_u32(sm + OFF_PE));
         c.w_lo = (uint32_t)umma_desc_sw128(smem_u32(sm + OFF_W));
         c.tmem_base = tmem_base;
+        c.ones_lo = desc_lo_noswz(smem_u32(sm + OFF_ONES));
+        c.bt_lo = desc_lo_noswz(smem_u32(sm + OFF_BT));
+        c.bslot = 0; c.bpar = 0;
         c.stage = 0; c.wpar = 0; c.layer_ctr = 0; c.iter_ctr = 0;
         c.t_e = c.t_w = c.t_pe = 0;
         const long long t_tot = clock64();
@@ -355,6 +390,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
         const uint32_t row_off = (row >> 3) * 1024 + (row & 7) * 128;
         const uint32_t rsw = row & 7;
         uint32_t layer_ctr = 0, iter_ctr = 0;
+        long long te_wait = 0, te_ld = 0, te_c1 = 0, te_st = 0;       // trace build: epilogue phase cycles (warp 4)
         for (long long it = blockIdx.x; it < n_iter; it += gridDim.x, ++iter_ctr) {
             const long long p0 = it * 256 + slot * 128;
             long long p = p0 + row;
@@ -369,33 +405,47 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                 if (l == 8) wait_or_report<TRACE>(&bars->dirb_ready, iter_ctr & 1, 301, l, (int)iter_ctr);
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
+                    long long q0 = 0;
+                    if constexpr (TRACE) q0 = clock64();
                     wait_or_report<TRACE>(&bars->cbar[h == 0 ? 0 : 2], par, 302 + h, l, (int)layer_ctr);
                     __syncwarp();
                     tc_fence_after();
+                    if constexpr (TRACE) { const long long q1 = clock64(); te_wait += q1 - q0; q0 = q1; }
                     uint32_t packed[64];
                     const int nchunk = NH >> 5;      // 4 (N=256) or 2 (N=128)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         if (c < nchunk && !(ABL & 1)) {
                             uint32_t r[32];
-                            tmem_ld32(t_lane + h * NH + c * 32, r);
-                            tmem_wait_ld();
+                            if constexpr (ABL & 8) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) r[j] = (uint32_t)(lane + j + l);
+                            } else {
+                                tmem_ld32(t_lane + h * NH + c * 32, r);
+                                tmem_wait_ld();
+                            }
+                            if constexpr (ABL & 16) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) packed[c * 16 + j] = r[j] ^ r[j + 16];
+                                continue;
+                            }
                             const int f0 = h * NH + c * 32;                 // first output feature of the chunk
-                            const float* bsrc = s_bias + li.bias_off + f0;
                             float* tr = TRACE ? trace + ((size_t)l * 256 + slot * 128 + row) * 256 + f0 : nullptr;
                             const bool dump = TRACE && it == 0;
                             switch (l) {                                    // layer kind is warp-uniform: one specialised body per chunk
-                                case 7: epi_convert<1, TRACE>(r, &packed[c * 16], bsrc, nullptr, s_aw + f0, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump); break;
-                                case 8: epi_convert<2, TRACE>(r, &packed[c * 16], bsrc, s_dirb + (slot * RMAX + ray_local) * 128 + f0, nullptr, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump); break;
-                                case 10: epi_convert<3, TRACE>(r, &packed[c * 16], bsrc, nullptr, nullptr, s_rw + f0, alpha, rgb0, rgb1, rgb2, tr, dump); break;
-                                default: epi_convert<0, TRACE>(r, &packed[c * 16], bsrc, nullptr, nullptr, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump); break;
+                                case 7: epi_convert<1, TRACE>(r, &packed[c * 16], nullptr, s_aw + f0, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump); break;
+                                case 8: epi_convert<2, TRACE>(r, &packed[c * 16], s_dirb + (slot * RMAX + ray_local) * 128 + f0, nullptr, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump); break;
+                                case 10: epi_convert<3, TRACE>(r, &packed[c * 16], nullptr, nullptr, s_rw + f0, alpha, rgb0, rgb1, rgb2, tr, dump); break;
+                                default: epi_convert<0, TRACE>(r, &packed[c * 16], nullptr, nullptr, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump); break;
                             }
                         }
                     }
                     tc_fence_before();
+                    if constexpr (TRACE) { const long long q1 = clock64(); te_ld += q1 - q0; q0 = q1; }
                     if (l != 10) {
                         if (h == 0) wait_or_report<TRACE>(&bars->cbar[1], par, 304, l, (int)layer_ctr);
                         __syncwarp();      // h1 has finished reading the K-blocks written below
+                        if constexpr (TRACE) { const long long q1 = clock64(); te_c1 += q1 - q0; q0 = q1; }
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             if (c < nchunk && !(ABL & 1)) {
@@ -416,6 +466,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                     // the layer-to-layer critical path (E1 gates the next layer's third K-block)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->ebar[h]);
+                    if constexpr (TRACE) te_st += clock64() - q0;
                 }
                 if (l == 8) {
                     __syncwarp();
@@ -424,11 +475,17 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
             }
             if (in_range) {
                 float4 o;
-                o.x = rgb0 + s_bias[8 * 256 + 3 * 128 + 1];
-                o.y = rgb1 + s_bias[8 * 256 + 3 * 128 + 2];
-                o.z = rgb2 + s_bias[8 * 256 + 3 * 128 + 3];
-                o.w = alpha + s_bias[8 * 256 + 3 * 128];
+                o.x = rgb0 + s_sb[1];
+                o.y = rgb1 + s_sb[2];
+                o.z = rgb2 + s_sb[3];
+                o.w = alpha + s_sb[0];
                 reinterpret_cast<float4*>(a.out)[p] = o;
+            }
+        }
+        if constexpr (TRACE) {
+            if (warp == 4 && lane == 0) {
+                float* t = trace + (size_t)11 * 256 * 256 + (148 + blockIdx.x) * 8;
+                t[0] = (float)te_wait; t[1] = (float)te_ld; t[2] = (float)te_c1; t[3] = (float)te_st; t[4] = (float)iter_ctr;
             }
         }
     } else if (warp >= 12) {
@@ -645,7 +702,7 @@ int mlp_bf16_hang_info(int32_t* out8) {
 int mlp_bf16_launch(const MlpArgs& a, bool embedded, cudaStream_t st) {
     if (embedded)
         return fail(INERF_E_UNSUPPORTED, "bf16 mode is built for the fused (rays, z) entry; FaceNeRF.forward on embedded rows runs in fp32 mode");
-    if (a.s < 32) return fail(INERF_E_UNSUPPORTED, "bf16 mode needs at least 32 samples per ray (a 128-row slot may touch at most 5 rays)");
+    if (a.s < 43) return fail(INERF_E_UNSUPPORTED, "bf16 mode needs at least 43 samples per ray (a 128-row slot may touch at most 4 rays)");
     if ((uintptr_t)a.packed & 15) return fail(INERF_E_ALIGN, "inerf_mlp_fwd: packed weights must be 16-byte aligned");
     static thread_local int configured_dev = -1;
     static Schedule S;
@@ -681,9 +738,9 @@ int mlp_bf16_launch(const MlpArgs& a, bool embedded, cudaStream_t st) {
         const int abl = atoi(e);
 #define ABL_CASE(N_) case N_: cudaFuncSetAttribute(mlp_bf16_kernel<false, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC); \
                               mlp_bf16_kernel<false, N_><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, nullptr); break;
-        switch (abl) { ABL_CASE(1) ABL_CASE(2) ABL_CASE(3) ABL_CASE(4) ABL_CASE(5) ABL_CASE(6) ABL_CASE(7) default: break; }
+        switch (abl) { ABL_CASE(1) ABL_CASE(2) ABL_CASE(3) ABL_CASE(4) ABL_CASE(5) ABL_CASE(6) ABL_CASE(7) ABL_CASE(8) ABL_CASE(16) ABL_CASE(24) default: break; }
 #undef ABL_CASE
-        if (abl >= 1 && abl <= 7) return check_launch("inerf_mlp_fwd[bf16,ablation]");
+        if (abl >= 1 && abl <= 24) return check_launch("inerf_mlp_fwd[bf16,ablation]");
     }
 #endif
     if (a.trace) mlp_bf16_kernel<true><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, a.trace);

@@ -14,6 +14,8 @@
 // Conditioning (aud | expr/3 | latent) is constant over the call, so its weight columns are folded
 // into the biases once per call by inerf_mlp_fold_cond and the per-point
 // network is 63->256, 4x(256->256), 319->256, 2x(256->256), {256->1, 283->128, 2x(128->128), 128->3}.
+#include <cuda_bf16.h>
+
 #include "mlp_common.cuh"
 
 using namespace inerf;
@@ -284,8 +286,20 @@ struct FoldArgs {
     float* cond;
 };
 
+// Row `r` of a bias tile for the tensor-core kernel (mlp_bf16.cu): K-major, non-swizzled [rows][16] bf16 stored as 8x8 core
+// matrices, columns (hi, lo, 0, ..., 0) with hi + lo = the fp32 bias to 16 mantissa bits.
+__device__ __forceinline__ void write_bias_tile_row(uint8_t* tile, int r, float b) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+    const uint32_t w0 = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+    uint8_t* p = tile + (r >> 3) * 256 + (r & 7) * 16;
+    *reinterpret_cast<uint4*>(p) = make_uint4(w0, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(p + 128) = make_uint4(0u, 0u, 0u, 0u);
+}
+
 __global__ void fold_cond_kernel(FoldArgs f) {
     __shared__ float c[1024];
+    uint8_t* tiles = reinterpret_cast<uint8_t*>(f.cond + CondLayout{256, 128}.total());
     const int C = f.da + f.de + f.dl;
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
         float v;
@@ -307,7 +321,10 @@ __global__ void fold_cond_kernel(FoldArgs f) {
             if (folded)
                 for (int j = lane; j < C; j += 32) s = fmaf(W[(size_t)n * ldw + 63 + j], c[j], s);
             s = warp_sum(s);
-            if (lane == 0) f.cond[cl.pts(b) + n] = B[n] + s;
+            if (lane == 0) {
+                f.cond[cl.pts(b) + n] = B[n] + s;
+                write_bias_tile_row(tiles + (2 * b + (n >> 7)) * 4096, n & 127, B[n] + s);
+            }
         }
     } else if (b < 11) {                          // views_linears.(b-8)
         const int v = b - 8;
@@ -319,7 +336,10 @@ __global__ void fold_cond_kernel(FoldArgs f) {
             if (v == 0)
                 for (int j = lane; j < f.de; j += 32) s = fmaf(W[(size_t)n * ldw + 283 + j], c[f.da + j], s);
             s = warp_sum(s);
-            if (lane == 0) f.cond[cl.views(v) + n] = B[n] + s;
+            if (lane == 0) {
+                f.cond[cl.views(v) + n] = B[n] + s;
+                write_bias_tile_row(tiles + 65536 + (2 * v + (n >> 6)) * 2048, n & 63, B[n] + s);
+            }
         }
     } else if (threadIdx.x < 4) {
         f.cond[cl.alpha_b() + threadIdx.x] = threadIdx.x == 0 ? f.w[P_ALPHA_B][0] : f.w[P_RGB_B][threadIdx.x - 1];
@@ -370,7 +390,8 @@ extern "C" int inerf_mlp_cond_floats(const InerfNetDims* dims, size_t* n_floats)
     int rc = check_dims(dims);
     if (rc) return rc;
     if (!n_floats) return fail(INERF_E_ARG, "inerf_mlp_cond_floats: NULL");
-    *n_floats = (size_t)CondLayout{256, 128}.total();
+    // the folded fp32 biases, then the same biases as bf16 (hi, lo) operand tiles of the tensor-core kernel: 16 x 4 KB + 6 x 2 KB
+    *n_floats = (size_t)CondLayout{256, 128}.total() + (16 * 4096 + 6 * 2048) / sizeof(float);
     return INERF_OK;
 }
 

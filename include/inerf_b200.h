@@ -157,7 +157,8 @@ int inerf_mlp_cond_floats(const InerfNetDims* dims, size_t* n_floats);
  * Replaces the three einops.repeat + torch.cat of face_nerf.py:44-56,69 (and `expr * 1 / 3`, :49).
  * params_host: INERF_N_PARAMS device pointers (host array).  aud/expr/latent may be NULL when the
  * corresponding dim is 0.  cond: device buffer of inerf_mlp_cond_floats floats holding every bias
- * of the folded network: [b0'(W) b1..b4 b5' b6 b7 | bV0'(W/2) bV1 bV2 | alpha_b(1) rgb_b(3)]. */
+ * of the folded network: [b0'(W) b1..b4 b5' b6 b7 | bV0'(W/2) bV1 bV2 | alpha_b(1) rgb_b(3)], followed by the same biases as
+ * bf16 (hi, lo) operand tiles for the tensor-core kernel (which adds them with one extra MMA per layer half). */
 int inerf_mlp_fold_cond(const InerfNetDims* dims, const float* const* params_host, const float* aud,
                         const float* expr, const float* latent, float* cond, void* stream);
 

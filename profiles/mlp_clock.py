@@ -29,3 +29,6 @@ with torch.no_grad():
         it = float(t[:148, 4].mean())
         print(f"trace launch {rep}: {ms:.3f} ms, issuer span {cyc / 1e6:.2f} Mcycles -> {cyc / ms / 1e3:.0f} MHz; per iteration: total {float(t[:148,0].mean())/it:.0f} "
               f"wait-E {float(t[:148,1].mean())/it:.0f} wait-PE {float(t[:148,2].mean())/it:.0f} wait-W {float(t[:148,3].mean())/it:.0f} cycles")
+        e = t[148:296]
+        print(f"   epilogue warp 4, per iteration (22 half-layers): wait-C0/C2 {float(e[:,0].mean())/it:.0f}  tmem-ld+convert {float(e[:,1].mean())/it:.0f}  "
+              f"wait-C1 {float(e[:,2].mean())/it:.0f}  st.shared+fence+arrive {float(e[:,3].mean())/it:.0f} cycles")
