@@ -30,7 +30,7 @@ aud, expr, lat = fr["aud"].to(dev), fr["expr"].to(dev), fr["latent"].to(dev)
 names = {0: "full kernel", 1: "epilogue off", 2: "weight streaming off", 4: "sincosf off", 3: "epilogue+weights off",
          5: "epilogue+sincosf off", 6: "weights+sincosf off", 7: "all three off (MMA issue + barrier protocol only)", 16: "epilogue: no bias/ReLU/convert math", 24: "epilogue: stores only", 8: "epilogue: no TMEM loads"}
 pts = rays.shape[0] * 192
-for abl in (0, 1, 8, 16, 24):
+for abl in (0, 1, 2, 4, 7):
     os.environ["INERF_ABL"] = str(abl)
     with torch.no_grad():
         for _ in range(2):

@@ -32,3 +32,5 @@ with torch.no_grad():
         e = t[148:296]
         print(f"   epilogue warp 4, per iteration (22 half-layers): wait-C0/C2 {float(e[:,0].mean())/it:.0f}  tmem-ld+convert {float(e[:,1].mean())/it:.0f}  "
               f"wait-C1 {float(e[:,2].mean())/it:.0f}  st.shared+fence+arrive {float(e[:,3].mean())/it:.0f} cycles")
+        lw = ops.mlp_fwd_trace.layer_waits.cpu()[:, :11].mean(0) / it
+        print("   issuer wait-E per layer (L0..L7, V0..V2):", " ".join(f"{float(x):.0f}" for x in lw))
