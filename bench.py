@@ -41,6 +41,16 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def mlp_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the MLP kernel, mean per launch over the coarse and the fine pass, from the
+    committed ncu --set full capture (profiles/); None when the summary is absent."""
+    p = os.path.join(ROOT, "profiles", "r01b_mlp_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))["dram_bytes_per_launch"]
+    return sum(d.values()) / len(d)
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -292,7 +302,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "inerf_mlp_fwd", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None, "traffic": mlp_traffic(),
                          "peak_kind": f"bf16 dense sustained, {pk_kind}", "launches": n_mlp, "kernel_ms_total": mlp_ms,
                          "share_of_step": mlp_ms / total_ms if total_ms else None},
             "roofline_composite": {"bound": "hbm", "kernel": "inerf_composite_fwd",

@@ -401,6 +401,98 @@ int check_case(int N) {
     return rc || bad;
 }
 
+
+// ---- MN-major operands: D[m][n] = sum_p A[p][m] * B[p][n] with A, B stored point-major as [128 points][64 features] 128B-swizzled
+// images (the layout the forward kernel keeps its activations in) -- the dW GEMM of the training path.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;      // next 64 MN elements
+    d |= (uint64_t)(1024 >> 4) << 32;           // next 8 K rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)SWIZZLE_128B << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(128, 1) mn_kernel(const uint8_t* a_img, const uint8_t* b_img, float* d, int N) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint64_t& bar_load = *reinterpret_cast<uint64_t*>(sm + 98304);
+    uint64_t& bar_done = *reinterpret_cast<uint64_t*>(sm + 98304 + 8);
+    uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(sm + 98304 + 16);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { mbar_init(&bar_load, 1); mbar_init(&bar_done, 1); fence_mbar_init(); }
+    if (warp == 1) tmem_alloc_cg<1>(&tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(&bar_load, 2 * 16384 + (N / 64) * 16384);
+        bulk_g2s(sm, a_img, 2 * 16384, &bar_load);
+        bulk_g2s(sm + 32768, b_img, (N / 64) * 16384, &bar_load);
+        bounded_wait(&bar_load, 0);
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_bf16(128, N) | (1u << 15) | (1u << 16);      // A and B MN-major
+        for (int k = 0; k < 8; ++k) {
+            const uint64_t ad = umma_desc_mn_sw128(smem_u32(sm) + k * 2048, 16384);
+            const uint64_t bd = umma_desc_mn_sw128(smem_u32(sm + 32768) + k * 2048, 16384);
+            mma<1, false>(tmem_base, ad, bd, idesc, k ? 1u : 0u);
+        }
+        commit<1>(&bar_done);
+    }
+    __syncwarp();
+    bounded_wait(&bar_done, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, r);
+        tmem_wait_ld();
+        for (int j = 0; j < 32; ++j) d[(size_t)(warp * 32 + lane) * N + c0 + j] = __uint_as_float(r[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc_cg<1>(tmem_base, 512);
+}
+
+int check_mn(int N) {
+    const int P = 128, M = 128;
+    std::vector<float> A((size_t)P * M), B((size_t)P * N), R((size_t)M * N), D((size_t)M * N);
+    srand(N + 99);
+    for (auto& v : A) v = (float)(rand() % 7 - 3);
+    for (auto& v : B) v = (float)(rand() % 7 - 3);
+    for (int m = 0; m < M; ++m)
+        for (int n = 0; n < N; ++n) {
+            float s = 0;
+            for (int p = 0; p < P; ++p) s += A[(size_t)p * M + m] * B[(size_t)p * N + n];
+            R[(size_t)m * N + n] = s;
+        }
+    std::vector<uint8_t> ai((size_t)2 * 16384), bi((size_t)(N / 64) * 16384);
+    for (int p = 0; p < P; ++p) {
+        for (int m = 0; m < M; ++m) { uint16_t h = f2bf(A[(size_t)p * M + m]); memcpy(&ai[(size_t)(m / 64) * 16384 + sw128_offset(p, m % 64)], &h, 2); }
+        for (int n = 0; n < N; ++n) { uint16_t h = f2bf(B[(size_t)p * N + n]); memcpy(&bi[(size_t)(n / 64) * 16384 + sw128_offset(p, n % 64)], &h, 2); }
+    }
+    uint8_t *da, *db; float* dd;
+    cudaMalloc(&da, ai.size()); cudaMalloc(&db, bi.size()); cudaMalloc(&dd, D.size() * 4);
+    cudaMemcpy(da, ai.data(), ai.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(db, bi.data(), bi.size(), cudaMemcpyHostToDevice);
+    cudaMemset(dd, 0xff, D.size() * 4);
+    cudaFuncSetAttribute(mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304 + 64);
+    mn_kernel<<<1, 128, 98304 + 64>>>(da, db, dd, N);
+    cudaError_t e = cudaDeviceSynchronize();
+    long bad = 0;
+    if (e != cudaSuccess) { printf("   CUDA error: %s\n", cudaGetErrorString(e)); bad = -1; }
+    else {
+        cudaMemcpy(D.data(), dd, D.size() * 4, cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < D.size(); ++i) bad += (D[i] != R[i]);
+        if (bad)
+            for (size_t i = 0, shown = 0; i < D.size() && shown < 4; ++i)
+                if (D[i] != R[i]) { printf("   [m=%zu n=%zu] got %g want %g\n", i / N, i % N, D[i], R[i]); ++shown; }
+    }
+    printf("check MN-major A/B (point-major images) N=%3d: %s (%ld mismatches)\n", N, bad ? "FAIL" : "ok", bad);
+    cudaFree(da); cudaFree(db); cudaFree(dd);
+    return bad != 0;
+}
+
 template <int CG, bool TS>
 void rate_case(int N, int slots, int interfere, int grid, int mimic = 0) {
     float* rep;
@@ -432,6 +524,9 @@ int main(int argc, char** argv) {
     fails += check_case<2, false>(256);
     fails += check_case<2, true>(256);
     fails += check_case<2, false>(128);
+    fails += check_mn(256);
+    fails += check_mn(64);
+    if (argc > 1) { printf(fails ? "UMMA checks: %d FAILED\n" : "UMMA checks passed\n", fails); return fails != 0; }
     const int G = 148;
     for (int inter = 0; inter <= 2; ++inter) {
         if (inter < 2) {
