@@ -146,12 +146,12 @@ def build_network(mode, dev):
     return M, net, fr, cam
 
 
-def train_step_bench(M, dev, steps):
+def train_step_bench(M, dev, steps, mode="bf16"):
     """BASELINE.json config 3: N_rand=3072 rays (64+128 samples), loss of audio_exp_nerf.py:540-548, backward through
-    compositing + both FaceNeRFs, Adam(lr=3e-4) step.  fp32 kernels (the bf16 tensor-core kernel is forward-only)."""
+    compositing + both FaceNeRFs, Adam(lr=3e-4) step.  mode: bf16 = tcgen05 forward-with-save + chain + dW kernels; fp32 = FFMA."""
     from ideal_nerf_b200 import synthetic as S, ops
     cam, fr = S.camera(), S.frame_inputs(0)
-    a = M.default_args(dim_aud=64, dim_expr=76, perturb=1.0, mlp_mode="fp32", N_samples=S1, N_importance=S_IMP)
+    a = M.default_args(dim_aud=64, dim_expr=76, perturb=1.0, mlp_mode=mode, N_samples=S1, N_importance=S_IMP)
     net = M.Network(H, W, cam["focal"], S.NEAR, S.FAR, 8192, None, S1, S_IMP, args=a)
     torch.manual_seed(4321)
     net.apply(M.init_weights)
@@ -184,7 +184,7 @@ def train_step_bench(M, dev, steps):
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    return {"rays_per_s": 3072 / (ms * 1e-3), "ms_per_step": ms, "n_rand": 3072, "mlp_mode": "fp32", "optimizer": "Adam lr=3e-4",
+    return {"rays_per_s": 3072 / (ms * 1e-3), "ms_per_step": ms, "n_rand": 3072, "mlp_mode": mode, "optimizer": "Adam lr=3e-4",
             "loss": float(loss), "gpu_launches_per_step": ops.LAUNCHES["count"] / steps,
             "kernels_ms_per_step": {k: round(v[1] / steps, 3) for k, v in kt.summary().items()}}
 
@@ -313,7 +313,8 @@ def run_ours(args):
             "kernels_ms": {k: round(v[1], 3) for k, v in ksum.items()},
         }
         if world == 1 and not args.no_train:
-            line["train_step"] = train_step_bench(M, dev, 3)
+            line["train_step"] = train_step_bench(M, dev, 5, "bf16")
+            line["train_step_fp32"] = train_step_bench(M, dev, 3, "fp32")
         if world == 1 and not args.no_cpu_baseline:
             v, dt, cores = cpu_reference_rays_per_s(3072, 2, 1)
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",

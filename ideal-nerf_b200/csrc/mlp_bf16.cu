@@ -137,16 +137,20 @@ __device__ __forceinline__ LayerInfo layer_info(int l) {
 
 // One 32-column chunk of an epilogue: +bias (+per-ray view bias), ReLU, bf16 pack; KIND 1 also accumulates
 // alpha_linear, KIND 3 rgb_linear, in fp32 from the un-rounded activations.
-template <int KIND, bool TRACE>
+template <int KIND, bool TRACE, bool SAVE>
 __device__ __forceinline__ void epi_convert(const uint32_t (&r)[32], uint32_t* __restrict__ packed16,
                                             const float* __restrict__ dsrc, const float* __restrict__ aw, const float* __restrict__ rw,
-                                            float& alpha, float& rgb0, float& rgb1, float& rgb2, float* tr, bool dump) {
+                                            float& alpha, float& rgb0, float& rgb1, float& rgb2, float* tr, bool dump, uint32_t& neg_bits) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
         float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])};
         if constexpr (KIND == 2) {
             const float4 d = *reinterpret_cast<const float4*>(dsrc + j);
             v[0] += d.x; v[1] += d.y; v[2] += d.z; v[3] += d.w;
+        }
+        if constexpr (SAVE) {      // sign bits, first value in the top bit: one funnel shift per value
+#pragma unroll
+            for (int t = 0; t < 4; ++t) neg_bits = __funnelshift_l(__float_as_uint(v[t]), neg_bits, 1);
         }
         if constexpr (KIND == 1) {
             const float4 w = *reinterpret_cast<const float4*>(aw + j);
@@ -287,7 +291,7 @@ __device__ __forceinline__ void issue_layer(IssueCtx& c) {
 // ABL (builds with -DINERF_ABLATION only; profiles/ablate_mlp.py): bit 0 = epilogue keeps its barrier protocol but skips the
 // TMEM loads / conversion / smem stores, bit 1 = weights are loaded once (no streaming, no full-barrier waits), bit 2 = the
 // positional-encoding warps skip sincosf, bit 3 = the epilogue skips only its TMEM loads, bit 4 = only its bias/ReLU/convert math.  Outputs are garbage; only the timing is meaningful.
-template <bool TRACE, int ABL = 0>
+template <bool TRACE, int ABL = 0, bool SAVE = false>
 __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, int n_steps, int n_rays, float* __restrict__ trace) {
     // Dynamic shared memory is the only shared allocation of this kernel, so it starts at offset 0 of the CTA's
     // window: 1024-byte aligned as the 128B-swizzle atoms need.  (No pointer re-alignment arithmetic here: it would
@@ -434,13 +438,25 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                                 continue;
                             }
                             const int f0 = h * NH + c * 32;                 // first output feature of the chunk
+                            uint32_t neg = 0;
                             float* tr = TRACE ? trace + ((size_t)l * 256 + slot * 128 + row) * 256 + f0 : nullptr;
                             const bool dump = TRACE && it == 0;
                             switch (l) {                                    // layer kind is warp-uniform: one specialised body per chunk
-                                case 7: epi_convert<1, TRACE>(r, &packed[c * 16], nullptr, s_aw + f0, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump); break;
-                                case 8: epi_convert<2, TRACE>(r, &packed[c * 16], s_dirb + (slot * RMAX + ray_local) * 128 + f0, nullptr, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump); break;
-                                case 10: epi_convert<3, TRACE>(r, &packed[c * 16], nullptr, nullptr, s_rw + f0, alpha, rgb0, rgb1, rgb2, tr, dump); break;
-                                default: epi_convert<0, TRACE>(r, &packed[c * 16], nullptr, nullptr, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump); break;
+                                case 7: epi_convert<1, TRACE, SAVE>(r, &packed[c * 16], nullptr, s_aw + f0, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump, neg); break;
+                                case 8: epi_convert<2, TRACE, SAVE>(r, &packed[c * 16], s_dirb + (slot * RMAX + ray_local) * 128 + f0, nullptr, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump, neg); break;
+                                case 10: epi_convert<3, TRACE, SAVE>(r, &packed[c * 16], nullptr, nullptr, s_rw + f0, alpha, rgb0, rgb1, rgb2, tr, dump, neg); break;
+                                default: epi_convert<0, TRACE, SAVE>(r, &packed[c * 16], nullptr, nullptr, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump, neg); break;
+                            }
+                            if constexpr (SAVE) {
+                                // training: the chunk as it goes to shared memory (same swizzled image, 4 x 16 B) + its ReLU mask word
+                                const size_t T = (size_t)it * 2 + slot;
+                                uint8_t* img = a.save_img + (T * TRAIN_IMGS + train_img_of(l) + (f0 >> 6)) * 16384 + row_off;
+                                const int ch0 = (f0 & 63) >> 3;
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    *reinterpret_cast<uint4*>(img + (((ch0 + q) ^ rsw) << 4)) =
+                                        make_uint4(packed[c * 16 + q * 4], packed[c * 16 + q * 4 + 1], packed[c * 16 + q * 4 + 2], packed[c * 16 + q * 4 + 3]);
+                                a.save_mask[(T * TRAIN_MASK_WORDS + train_mask_of(l) + (f0 >> 5)) * 128 + row] = ~neg;
                             }
                         }
                     }
@@ -548,6 +564,16 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
             }
             fence_proxy_async_smem();
             mbar_arrive(&bars->pe_ready);
+            if constexpr (SAVE) {          // training: gamma(p) is the X operand of dW for pts_linears.0 / .5
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl) {
+                    uint8_t* dst = a.save_img + (((size_t)it * 2 + sl) * TRAIN_IMGS + TRAIN_IMG_PE) * 16384 + (t >> 3) * 1024 + (t & 7) * 128;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<uint4*>(dst + ((q ^ (t & 7)) << 4)) =
+                            make_uint4(pk[sl][4 * q], pk[sl][4 * q + 1], pk[sl][4 * q + 2], pk[sl][4 * q + 3]);
+                }
+            }
             // ---- per-ray view bias: lane q < 2*RMAX encodes ray q, the warp shares it by shuffle ----
             {
                 float enc[27];
@@ -572,6 +598,30 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                 } else {
 #pragma unroll
                     for (int j = 0; j < 27; ++j) enc[j] = 0.f;
+                }
+                if constexpr (SAVE) {      // training: gamma(v) per POINT, the X operand of dW for the view columns of views_linears.0
+#pragma unroll
+                    for (int sl = 0; sl < 2; ++sl) {
+                        long long p = it * 256 + sl * 128 + t, pfirst = it * 256 + sl * 128;
+                        if (p > a.P - 1) p = a.P - 1;
+                        if (pfirst > a.P - 1) pfirst = a.P - 1;
+                        const int src = sl * RMAX + (int)(p / a.s - pfirst / a.s);
+                        float g[28];
+#pragma unroll
+                        for (int j = 0; j < 27; ++j) g[j] = __shfl_sync(0xffffffffu, enc[j], src);
+                        g[27] = 0.f;
+                        uint8_t* dst = a.save_img + (((size_t)it * 2 + sl) * TRAIN_IMGS + TRAIN_IMG_DIR) * 16384 + (t >> 3) * 1024 + (t & 7) * 128;
+#pragma unroll
+                        for (int qq = 0; qq < 8; ++qq) {
+                            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                            if (qq < 4) {
+                                v.x = pack_bf16x2(g[8 * qq], g[8 * qq + 1]);
+                                v.y = pack_bf16x2(g[8 * qq + 2], g[8 * qq + 3]);
+                                if (qq < 3) { v.z = pack_bf16x2(g[8 * qq + 4], g[8 * qq + 5]); v.w = pack_bf16x2(g[8 * qq + 6], g[8 * qq + 7]); }
+                            }
+                            *reinterpret_cast<uint4*>(dst + ((qq ^ (t & 7)) << 4)) = v;
+                        }
+                    }
                 }
                 if (iter_ctr > 0) wait_or_report<TRACE>(&bars->dirb_free, (iter_ctr - 1) & 1, 402, 0, (int)iter_ctr);
                 for (int q2 = 0; q2 < 2 * RMAX; ++q2) {
@@ -755,6 +805,17 @@ int mlp_bf16_launch(const MlpArgs& a, bool embedded, cudaStream_t st) {
         if (abl >= 1 && abl <= 24) return check_launch("inerf_mlp_fwd[bf16,ablation]");
     }
 #endif
+    if (a.save_img) {
+        if (!a.save_mask) return fail(INERF_E_ARG, "mlp_bf16: save_mask is NULL");
+        static thread_local int save_dev = -1;
+        if (save_dev != dev) {
+            cudaError_t e = cudaFuncSetAttribute(mlp_bf16_kernel<false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+            if (e != cudaSuccess) { set_error("mlp_bf16: setup: %s", cudaGetErrorString(e)); return (int)e; }
+            save_dev = dev;
+        }
+        mlp_bf16_kernel<false, 0, true><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, nullptr);
+        return check_launch("inerf_mlp_fwd_train[bf16]");
+    }
     if (a.trace) mlp_bf16_kernel<true><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, a.trace);
     else mlp_bf16_kernel<false><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, nullptr);
     return check_launch("inerf_mlp_fwd[bf16]");

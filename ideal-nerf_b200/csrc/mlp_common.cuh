@@ -25,15 +25,35 @@ struct MlpArgs {
     int dim_expr;
     float* save;                      // optional (fp32 path, training): activation store [ceil(P/64)*64][SAVE_W]
     float* trace;                     // optional (bf16 path): post-activation values of the first 256 points, [11][256][256]
+    // optional (bf16 path, training): per 128-point tile T = point/128, the activations as the forward kernel holds them in shared
+    // memory -- TRAIN_IMGS 16 KB images [128 points][64 features] bf16, K-major, 128-byte swizzle -- and the ReLU masks
+    uint8_t* save_img;                // [n_tiles][TRAIN_IMGS][16384]
+    uint32_t* save_mask;              // [n_tiles][TRAIN_MASK_WORDS][128]: bit (31-j) of word w = pre-activation 32w+j of the row is >= 0
 };
 
+// image index inside a tile: h0..h7 at 4l+kb, v0..v2 at 32+2v+kb, gamma(p) (63 cols) at 38, gamma(v) (27 cols) at 39; the backward
+// kernels store the deltas with the same map and d_raw (r,g,b,sigma in columns 0..3) at 38
+constexpr int TRAIN_IMGS = 40, TRAIN_IMG_PE = 38, TRAIN_IMG_DIR = 39, TRAIN_IMG_DOUT = 38, TRAIN_MASK_WORDS = 76;
+__host__ __device__ constexpr int train_img_of(int l) { return l < 8 ? 4 * l : 32 + 2 * (l - 8); }
+__host__ __device__ constexpr int train_mask_of(int l) { return l < 8 ? 8 * l : 64 + 4 * (l - 8); }
+
 int mlp_fp32_launch(const MlpArgs& a, bool embedded, cudaStream_t st);
-int mlp_bf16_launch(const MlpArgs& a, bool embedded, cudaStream_t st);
+int mlp_bf16_launch(const MlpArgs& a, bool embedded, cudaStream_t st);     // a.save_img != NULL: the activation-saving build
 int mlp_fp32_bwd_launch(const InerfNetDims* dims, const float* const* params_host, float* const* grads_host,
                         const float* aud, const float* expr, const float* latent, const float* acts, float* deltas,
                         const float* d_raw, long long P, float* d_cond, void* dw_args_dev, cudaStream_t st);
 size_t mlp_fp32_bwd_args_bytes();
 int mlp_bf16_hang_info(int32_t* out8);
+// bf16 training path (mlp_bf16_bwd.cu, mlp_bf16_dw.cu, mlp_fp32_bwd.cu)
+int mlp_bf16_bwd_packed_bytes(const InerfNetDims* d, size_t* bytes);
+int mlp_bf16_bwd_pack(const InerfNetDims* d, const float* const* params_host, void* packed, cudaStream_t st);
+int mlp_bf16_bwd_chain_launch(const InerfNetDims* dims, const float* const* params_host, const void* packed_t, const uint32_t* mask,
+                              const float* d_raw, uint8_t* delta_img, long long P, cudaStream_t st);
+size_t mlp_bf16_dw_scratch_bytes();
+int mlp_bf16_dw_launch(const InerfNetDims* dims, float* const* grads_host, const uint8_t* delta_img, const uint8_t* acts_img,
+                       long long n_tiles, void* scratch, cudaStream_t st);
+int mlp_bwd_cond_launch(const InerfNetDims* dims, const float* const* params_host, float* const* grads_host, const float* aud,
+                        const float* expr, const float* latent, float* d_cond, cudaStream_t st);
 int mlp_bf16_packed_bytes(const InerfNetDims* d, size_t* bytes);
 int mlp_bf16_pack(const InerfNetDims* d, const float* const* params_host, void* packed, cudaStream_t st);
 

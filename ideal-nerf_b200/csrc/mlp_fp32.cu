@@ -420,6 +420,7 @@ extern "C" int inerf_mlp_packed_bytes(int mode, const InerfNetDims* dims, size_t
     if (!bytes) return fail(INERF_E_ARG, "inerf_mlp_packed_bytes: NULL");
     if (mode == INERF_MLP_FP32) { *bytes = 0; return INERF_OK; }
     if (mode == INERF_MLP_BF16) return mlp_bf16_packed_bytes(dims, bytes);
+    if (mode == INERF_MLP_BF16_BWD) return mlp_bf16_bwd_packed_bytes(dims, bytes);
     return fail(INERF_E_UNSUPPORTED, "inerf_mlp_packed_bytes: unknown mode");
 }
 
@@ -431,6 +432,10 @@ extern "C" int inerf_mlp_pack(int mode, const InerfNetDims* dims, const float* c
     if (mode == INERF_MLP_BF16) {
         if (!params_host || !packed) return fail(INERF_E_ARG, "inerf_mlp_pack: NULL pointer");
         return mlp_bf16_pack(dims, params_host, packed, as_stream(stream));
+    }
+    if (mode == INERF_MLP_BF16_BWD) {
+        if (!params_host || !packed) return fail(INERF_E_ARG, "inerf_mlp_pack: NULL pointer");
+        return mlp_bf16_bwd_pack(dims, params_host, packed, as_stream(stream));
     }
     return fail(INERF_E_UNSUPPORTED, "inerf_mlp_pack: unknown mode");
 }
@@ -543,4 +548,63 @@ extern "C" int inerf_mlp_fwd_embedded(int mode, const InerfNetDims* dims, const 
         return mlp_bf16_launch(a, true, as_stream(stream));
     }
     return fail(INERF_E_UNSUPPORTED, "inerf_mlp_fwd_embedded: unknown mode");
+}
+
+// ---- training, bf16 tensor-core mode -----------------------------------------------------------------------------------------
+
+extern "C" int inerf_mlp_train_sizes_bf16(const InerfNetDims* dims, int64_t n_points, size_t* acts_bytes, size_t* mask_bytes,
+                                          size_t* deltas_bytes, size_t* scratch_bytes) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (n_points < 0 || !acts_bytes || !mask_bytes || !deltas_bytes || !scratch_bytes) return fail(INERF_E_ARG, "inerf_mlp_train_sizes_bf16: bad argument");
+    const size_t n_tiles = (size_t)((n_points + 255) / 256) * 2;          // 128-point tiles, two per kernel iteration
+    *acts_bytes = n_tiles * TRAIN_IMGS * 16384;
+    *deltas_bytes = n_tiles * TRAIN_IMGS * 16384;
+    *mask_bytes = n_tiles * TRAIN_MASK_WORDS * 128 * sizeof(uint32_t);
+    *scratch_bytes = mlp_bf16_dw_scratch_bytes();
+    return INERF_OK;
+}
+
+extern "C" int inerf_mlp_fwd_train_bf16(const InerfNetDims* dims, const float* const* params_host, const void* packed, const float* cond,
+                                        const float* rays, int ray_stride, const float* z, int n, int s, float* raw, void* acts,
+                                        void* mask, void* stream) {
+    MlpArgs a{};
+    int rc = fill_args(a, dims, params_host, cond);
+    if (rc) return rc;
+    if (n < 0 || s <= 0 || ray_stride < 11) return fail(INERF_E_SHAPE, "inerf_mlp_fwd_train_bf16: bad n/s/ray_stride");
+    if (n == 0) return INERF_OK;
+    if (!rays || !z || !raw || !packed || !acts || !mask) return fail(INERF_E_ARG, "inerf_mlp_fwd_train_bf16: NULL pointer");
+    if (((uintptr_t)raw | (uintptr_t)acts | (uintptr_t)mask) & 15) return fail(INERF_E_ALIGN, "inerf_mlp_fwd_train_bf16: raw/acts/mask must be 16-byte aligned");
+    a.rays = rays; a.ray_stride = ray_stride; a.z = z; a.s = s; a.P = (long long)n * s; a.out = raw; a.packed = packed;
+    a.save_img = reinterpret_cast<uint8_t*>(acts); a.save_mask = reinterpret_cast<uint32_t*>(mask);
+    return mlp_bf16_launch(a, false, as_stream(stream));
+}
+
+extern "C" int inerf_mlp_bwd_bf16(const InerfNetDims* dims, const float* const* params_host, const void* packed_t,
+                                  float* const* grads_host, const float* aud, const float* expr, const float* latent, const void* acts,
+                                  const void* mask, void* deltas, const float* d_raw, int64_t n_points, float* d_cond, void* scratch,
+                                  void* stream) {
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (n_points < 0) return fail(INERF_E_SHAPE, "inerf_mlp_bwd_bf16: n_points < 0");
+    if (n_points == 0) return INERF_OK;
+    if (!params_host || !grads_host || !packed_t || !acts || !mask || !deltas || !d_raw || !scratch) return fail(INERF_E_ARG, "inerf_mlp_bwd_bf16: NULL pointer");
+    for (int i = 0; i < INERF_N_PARAMS; ++i)
+        if (!params_host[i] || !grads_host[i]) return fail(INERF_E_ARG, "inerf_mlp_bwd_bf16: NULL parameter/gradient pointer");
+    const int C = dims->dim_aud + dims->dim_expr + dims->dim_latent;
+    if (C > 0 && !d_cond) return fail(INERF_E_ARG, "inerf_mlp_bwd_bf16: d_cond is NULL");
+    if ((dims->dim_aud > 0 && !aud) || (dims->dim_expr > 0 && !expr) || (dims->dim_latent > 0 && !latent))
+        return fail(INERF_E_ARG, "inerf_mlp_bwd_bf16: conditioning vector missing for a non-zero dim");
+    if (((uintptr_t)acts | (uintptr_t)deltas | (uintptr_t)d_raw | (uintptr_t)packed_t | (uintptr_t)mask) & 15)
+        return fail(INERF_E_ALIGN, "inerf_mlp_bwd_bf16: buffers must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    rc = mlp_bf16_bwd_chain_launch(dims, params_host, packed_t, reinterpret_cast<const uint32_t*>(mask), d_raw,
+                                   reinterpret_cast<uint8_t*>(deltas), n_points, st);
+    if (rc) return rc;
+    const long long n_tiles = ((n_points + 255) / 256) * 2;
+    rc = mlp_bf16_dw_launch(dims, grads_host, reinterpret_cast<const uint8_t*>(deltas), reinterpret_cast<const uint8_t*>(acts), n_tiles,
+                            scratch, st);
+    if (rc) return rc;
+    if (C > 0) rc = mlp_bwd_cond_launch(dims, params_host, grads_host, aud, expr, latent, d_cond, st);
+    return rc;
 }

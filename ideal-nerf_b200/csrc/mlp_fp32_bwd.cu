@@ -395,17 +395,22 @@ int mlp_fp32_bwd_launch(const InerfNetDims* dims, const float* const* params_hos
     rc = check_launch("inerf_mlp_bwd[dW]");
     if (rc) return rc;
 
-    if (C > 0) {
-        CondBwdArgs c{};
-        c.w[0] = params_host[0]; c.w[1] = params_host[10]; c.w[2] = params_host[P_VIEWS_W];
-        c.gw[0] = grads_host[0]; c.gw[1] = grads_host[10]; c.gw[2] = grads_host[P_VIEWS_W];
-        c.gb[0] = grads_host[1]; c.gb[1] = grads_host[11]; c.gb[2] = grads_host[P_VIEWS_W + 1];
-        c.aud = aud; c.expr = expr; c.latent = latent;
-        c.da = dims->dim_aud; c.de = E; c.dl = dims->dim_latent; c.d_cond = d_cond;
-        mlp_bwd_cond_kernel<<<E > 0 ? 3 : 2, 256, 0, st>>>(c);
-        rc = check_launch("inerf_mlp_bwd[cond]");
-    }
+    if (C > 0) rc = mlp_bwd_cond_launch(dims, params_host, grads_host, aud, expr, latent, d_cond, st);
     return rc;
+}
+
+// Gradients of the folded conditioning columns from the bias gradients of pts_linears.0 / .5 and views_linears.0 (both MLP modes).
+int mlp_bwd_cond_launch(const InerfNetDims* dims, const float* const* params_host, float* const* grads_host, const float* aud,
+                        const float* expr, const float* latent, float* d_cond, cudaStream_t st) {
+    const int E = dims->dim_expr;
+    CondBwdArgs c{};
+    c.w[0] = params_host[0]; c.w[1] = params_host[10]; c.w[2] = params_host[P_VIEWS_W];
+    c.gw[0] = grads_host[0]; c.gw[1] = grads_host[10]; c.gw[2] = grads_host[P_VIEWS_W];
+    c.gb[0] = grads_host[1]; c.gb[1] = grads_host[11]; c.gb[2] = grads_host[P_VIEWS_W + 1];
+    c.aud = aud; c.expr = expr; c.latent = latent;
+    c.da = dims->dim_aud; c.de = E; c.dl = dims->dim_latent; c.d_cond = d_cond;
+    mlp_bwd_cond_kernel<<<E > 0 ? 3 : 2, 256, 0, st>>>(c);
+    return check_launch("inerf_mlp_bwd[cond]");
 }
 
 size_t mlp_fp32_bwd_args_bytes() { return sizeof(DwArgs); }

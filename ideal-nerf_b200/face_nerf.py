@@ -71,6 +71,14 @@ class FaceNeRF(nn.Module):
             self._packed_key = key
         return self._packed
 
+    def packed_weights_bwd(self, params):
+        """Transposed stage images for the bf16 backward chain (re-packed when a parameter changed)."""
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if key != getattr(self, "_packed_t_key", None):
+            self._packed_t = ops.pack_weights(_lib.INERF_MLP_BF16_BWD, self._dims, [p.detach() for p in params])
+            self._packed_t_key = key
+        return self._packed_t
+
     def _prep(self, aud, expr, latent_code):
         params = self.kernel_params()
         for p in params:
@@ -102,8 +110,8 @@ class FaceNeRF(nn.Module):
 
 class _MlpFn(torch.autograd.Function):
     """run_network + FaceNeRF as one op.  Inference: one fused kernel in the module's mlp_mode.  Training (any
-    parameter or conditioning vector requires grad): the fp32 kernel keeps its activations and backward() runs the
-    analytic gradient kernels (csrc/mlp_fp32_bwd.cu)."""
+    parameter or conditioning vector requires grad): the forward keeps its activations and backward() runs the analytic
+    gradient kernels -- fp32 FFMA (csrc/mlp_fp32_bwd.cu) or bf16 tcgen05 (csrc/mlp_bf16_bwd.cu + mlp_bf16_dw.cu) by mlp_mode."""
 
     @staticmethod
     def forward(ctx, net, flags, a, b, aud, expr, latent, *params):
@@ -114,11 +122,18 @@ class _MlpFn(torch.autograd.Function):
         aud_d, expr_d, lat_d = f(aud), f(expr), f(latent)
         cond = ops.fold_cond(net._dims, pd, aud_d, expr_d, lat_d)
         if train:
-            if mode != _lib.INERF_MLP_FP32:
-                raise NotImplementedError("training runs in mlp_mode='fp32' (the bf16 tensor-core kernel is forward-only)")
+            ctx.net, ctx.has = net, (aud is not None, expr is not None, latent is not None)
+            if mode == _lib.INERF_MLP_BF16:
+                if embedded:
+                    raise NotImplementedError("bf16 training runs through the fused (rays, z) entry; FaceNeRF.forward on embedded rows trains in mlp_mode='fp32'")
+                out, acts, mask, n_points = ops.mlp_fwd_train_bf16(net._dims, pd, net.packed_weights(params), cond, a, b)
+                ctx.n_points, ctx.bf16 = n_points, True
+                ctx.save_for_backward(acts, mask, *[t for t in (aud_d, expr_d, lat_d) if t is not None], *pd)
+                ctx.packed_t = net.packed_weights_bwd(params)
+                return out
             out, acts, n_points = ops.mlp_fwd_train(net._dims, pd, cond, x=a) if embedded else \
                 ops.mlp_fwd_train(net._dims, pd, cond, rays=a, z=b)
-            ctx.net, ctx.n_points, ctx.has = net, n_points, (aud is not None, expr is not None, latent is not None)
+            ctx.n_points, ctx.bf16 = n_points, False
             ctx.save_for_backward(acts, *[t for t in (aud_d, expr_d, lat_d) if t is not None], *pd)
             return out
         packed = net.packed_weights(params)
@@ -130,12 +145,16 @@ class _MlpFn(torch.autograd.Function):
     def backward(ctx, g):
         saved = list(ctx.saved_tensors)
         acts = saved.pop(0)
+        mask = saved.pop(0) if ctx.bf16 else None
         aud = saved.pop(0) if ctx.has[0] else None
         expr = saved.pop(0) if ctx.has[1] else None
         latent = saved.pop(0) if ctx.has[2] else None
         params = saved
         d = ctx.net._dims
-        grads, d_cond = ops.mlp_bwd(d, params, aud, expr, latent, acts, g, ctx.n_points)
+        if ctx.bf16:
+            grads, d_cond = ops.mlp_bwd_bf16(d, params, ctx.packed_t, aud, expr, latent, acts, mask, g, ctx.n_points)
+        else:
+            grads, d_cond = ops.mlp_bwd(d, params, aud, expr, latent, acts, g, ctx.n_points)
         da, de = d.dim_aud, d.dim_expr
         g_aud = d_cond[:da] if aud is not None else None
         g_expr = d_cond[da:da + de] if expr is not None else None

@@ -349,6 +349,55 @@ def mlp_bwd(dims, params, aud, expr, latent, acts, d_raw, n_points):
     return grads, d_cond
 
 
+def _train_sizes_bf16(dims, n_points):
+    sizes = [ctypes.c_size_t() for _ in range(4)]
+    check(_lib.lib().inerf_mlp_train_sizes_bf16(ctypes.byref(dims), n_points, *[ctypes.byref(v) for v in sizes]), "inerf_mlp_train_sizes_bf16")
+    return [v.value for v in sizes]          # acts, mask, deltas, scratch (bytes)
+
+
+def mlp_fwd_train_bf16(dims, params, packed, cond, rays, z):
+    """bf16 tensor-core forward that keeps the activation images + ReLU masks for mlp_bwd_bf16.  Returns (raw, acts, mask, n_points)."""
+    rays, z = f32c(rays, "rays"), f32c(z, "z_vals")
+    n, s = z.shape
+    n_points, dev = n * s, z.device
+    acts_b, mask_b, _, _ = _train_sizes_bf16(dims, n_points)
+    raw = torch.empty((n, s, 4), device=dev)
+    acts = torch.empty((acts_b,), device=dev, dtype=torch.uint8)
+    mask = torch.empty((mask_b,), device=dev, dtype=torch.uint8)
+    arr = param_array(params)
+    with torch.cuda.device(dev):
+        call("inerf_mlp_fwd_train", _lib.lib().inerf_mlp_fwd_train_bf16, ctypes.byref(dims), arr, ptr(packed), ptr(cond), ptr(rays),
+             rays.shape[1], ptr(z), n, s, ptr(raw), ptr(acts), ptr(mask), stream())
+    return raw, acts, mask, n_points
+
+
+def mlp_bwd_bf16(dims, params, packed_t, aud, expr, latent, acts, mask, d_raw, n_points, keep_deltas=False):
+    """bf16 tensor-core backward of FaceNeRF.  Returns (grads[26] fp32 in nn.Linear layout, d_cond [aud|expr|latent])."""
+    dev = acts.device
+    _, _, deltas_b, scratch_b = _train_sizes_bf16(dims, n_points)
+    deltas = torch.empty((deltas_b,), device=dev, dtype=torch.uint8)
+    scratch = torch.empty((scratch_b,), device=dev, dtype=torch.uint8)
+    grads = [torch.zeros_like(p) for p in params]
+    d_cond = torch.zeros((max(1, dims.dim_aud + dims.dim_expr + dims.dim_latent),), device=dev)
+    d_raw = f32c(d_raw, "d_raw").reshape(-1, 4)
+    parr, garr = param_array(params), param_array(grads)
+    with torch.cuda.device(dev):
+        call("inerf_mlp_bwd", _lib.lib().inerf_mlp_bwd_bf16, ctypes.byref(dims), parr, ptr(packed_t), garr, ptr(aud), ptr(expr), ptr(latent),
+             ptr(acts), ptr(mask), ptr(deltas), ptr(d_raw), n_points, ptr(d_cond), ptr(scratch), stream())
+    if keep_deltas:
+        mlp_bwd_bf16.deltas = deltas
+    return grads, d_cond
+
+
+def decode_images(buf, n_tiles, n_imgs=40):
+    """Test helper: [n_tiles][n_imgs] 16 KB images (128 rows x 64 bf16, 128-byte swizzle) -> float tensor (n_tiles, n_imgs, 128, 64)."""
+    b = buf[: n_tiles * n_imgs * 16384].view(torch.bfloat16).reshape(n_tiles, n_imgs, 128, 8, 8)      # row, 16-byte chunk, element
+    r = torch.arange(128, device=buf.device) & 7
+    idx = (torch.arange(8, device=buf.device)[None, :] ^ r[:, None])                                    # logical chunk c lives at c ^ (row & 7)
+    out = torch.gather(b, 3, idx[None, None, :, :, None].expand(n_tiles, n_imgs, 128, 8, 8))
+    return out.reshape(n_tiles, n_imgs, 128, 64).float()
+
+
 def mlp_fwd_trace(mode, dims, params, packed, cond, rays, z):
     """bf16 kernel with the per-layer activation trace of the first 256 points: returns (raw, trace[11,256,256])."""
     rays, z = f32c(rays, "rays"), f32c(z, "z_vals")

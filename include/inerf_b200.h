@@ -41,7 +41,8 @@ enum {
 /* MLP arithmetic modes (north_star: fp32 gate <= 1e-3 max-abs, bf16-MLP gate <= 0.05 dB PSNR) */
 enum {
     INERF_MLP_FP32 = 0, /* fp32 FFMA, weights read in nn.Linear layout                         */
-    INERF_MLP_BF16 = 1  /* bf16 operands, fp32 accumulate in TMEM, tcgen05.mma (packed weights) */
+    INERF_MLP_BF16 = 1, /* bf16 operands, fp32 accumulate in TMEM, tcgen05.mma (packed weights) */
+    INERF_MLP_BF16_BWD = 2 /* inerf_mlp_packed_bytes / inerf_mlp_pack only: the TRANSPOSED stage images of the bf16 backward chain */
 };
 
 /* sample_pdf summation policies */
@@ -205,6 +206,21 @@ int inerf_mlp_fwd_train(const InerfNetDims* dims, const float* const* params_hos
 int inerf_mlp_bwd(const InerfNetDims* dims, const float* const* params_host, float* const* grads_host, const float* aud,
                   const float* expr, const float* latent, const float* acts, float* deltas, const float* d_raw,
                   int64_t n_points, float* d_cond, void* scratch, void* stream);
+
+/* ---- training (bf16 tensor-core mode) ---------------------------------------------------------------------------------------
+ * Same contract as the fp32 pair above, with bf16 operands on tcgen05: the forward keeps every post-ReLU activation as the 16 KB
+ * shared-memory images of its own A operands plus one ReLU-mask bit per activation; the backward is a fused chain kernel
+ * (delta_{l-1} = delta_l . W_l * mask, weights streamed TRANSPOSED, inerf_mlp_pack mode INERF_MLP_BF16_BWD), one long-K tcgen05 GEMM
+ * per weight matrix for dW / db straight from those images, and the fp32 conditioning kernel.  Needs n*s points with s >= 43. */
+int inerf_mlp_train_sizes_bf16(const InerfNetDims* dims, int64_t n_points, size_t* acts_bytes, size_t* mask_bytes,
+                               size_t* deltas_bytes, size_t* scratch_bytes);
+int inerf_mlp_fwd_train_bf16(const InerfNetDims* dims, const float* const* params_host, const void* packed, const float* cond,
+                             const float* rays, int ray_stride, const float* z, int n, int s, float* raw, void* acts, void* mask,
+                             void* stream);
+/* grads_host: ZERO-INITIALISED gradient tensors (nn.Linear layout, fp32); d_cond as in inerf_mlp_bwd. */
+int inerf_mlp_bwd_bf16(const InerfNetDims* dims, const float* const* params_host, const void* packed_t, float* const* grads_host,
+                       const float* aud, const float* expr, const float* latent, const void* acts, const void* mask, void* deltas,
+                       const float* d_raw, int64_t n_points, float* d_cond, void* scratch, void* stream);
 
 /* After a failed inerf_mlp_fwd_trace (the trace build bounds every mbarrier wait to ~1 s and traps): the record
  * of the first waiter that timed out, {site code, block, thread, aux0, aux1, parity, 0, 0}; all zero otherwise.

@@ -561,3 +561,201 @@ def test_training_loop_reduces_loss(M):
         losses.append(float(loss))
     print("losses", losses)
     assert losses[-1] < losses[0] and all(np.isfinite(losses))
+
+
+# ------------------------------------------------------------------------------------------------
+# training, bf16 tensor-core mode: forward-with-save + chain + dW kernels
+# ------------------------------------------------------------------------------------------------
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def _emulated_bf16_forward(sd, pts_enc, dir_enc, aud, expr, lat):
+    """The bf16 kernel's arithmetic restated in torch (autograd-able): bf16-rounded weights and activations, fp32 accumulation,
+    fp32 biases (the kernel adds them as hi+lo bf16 pairs), fp32 gamma(v) bias, fp32 alpha / rgb heads."""
+    cond = torch.cat([aud, expr / 3.0, lat])
+    W = lambda k: sd[k]
+    ste = lambda w: w + (_bf(w) - w).detach()                              # value = bf16(w), gradient = identity
+    x = ste(pts_enc)
+    h = torch.relu(x @ ste(W("pts_linears.0.weight")[:, :63]).T + W("pts_linears.0.weight")[:, 63:] @ cond + W("pts_linears.0.bias"))
+    for l in range(1, 8):
+        hq = ste(h)
+        w = W(f"pts_linears.{l}.weight")
+        if l == 5:
+            C = cond.numel()
+            pre = x @ ste(w[:, :63]).T + w[:, 63:63 + C] @ cond + hq @ ste(w[:, 63 + C:]).T + W(f"pts_linears.{l}.bias")
+        else:
+            pre = hq @ ste(w).T + W(f"pts_linears.{l}.bias")
+        h = torch.relu(pre)
+    sigma = h @ W("alpha_linear.weight").T + W("alpha_linear.bias")        # fp32 head on the un-rounded activations
+    w = W("views_linears.0.weight")
+    v = torch.relu(ste(h) @ ste(w[:, :256]).T + dir_enc @ w[:, 256:283].T + w[:, 283:] @ (expr / 3.0) + W("views_linears.0.bias"))
+    for l in (1, 2):
+        v = torch.relu(ste(v) @ ste(W(f"views_linears.{l}.weight")).T + W(f"views_linears.{l}.bias"))
+    rgb = v @ W("rgb_linear.weight").T + W("rgb_linear.bias")
+    return torch.cat([rgb, sigma], -1)
+
+
+def _img_cols(A, first, n_img):
+    """(T, imgs, 128, 64) decoded images -> (T*128, 64*n_img) point-major columns."""
+    return A[:, first:first + n_img].permute(0, 2, 1, 3).reshape(-1, 64 * n_img)
+
+
+def _lay_img(l):
+    return (4 * l, 4) if l < 8 else (32 + 2 * (l - 8), 2)
+
+
+@pytest.mark.parametrize("n,s", [(301, 64), (40, 192), (47, 45)])
+def test_bf16_training_kernels_self_consistent(M, n, s):
+    """Each bf16 training kernel against torch on the kernel's OWN stored operands (identical ReLU masks, so the bound is bf16 rounding,
+    not mask flips): saved masks == (saved activation > 0); chain delta_{l-1} == bf16((delta_l . bf16(W_l)) * mask); dW == delta^T X;
+    db == sum delta; ragged last tile (n*s is not a multiple of 256) contributes nothing."""
+    ops = M.ops
+    b = O.synthetic_train_batch(0)
+    rays = b["rays"][:n].to(DEV)
+    sd = O.init_face_nerf(7)
+    net = head_net(M, sd, "bf16")
+    aud, expr, lat = b["aud"].to(DEV), b["expr"].to(DEV), b["latent"].to(DEV)
+    gen = torch.Generator(device=DEV).manual_seed(n)
+    z = ops.sample_coarse(rays, s, torch.rand(n, s, device=DEV, generator=gen))
+    G = torch.randn(n, s, 4, device=DEV, generator=gen) * torch.tensor([1., 1., 1., 0.3], device=DEV)
+    P = n * s
+    T = ((P + 255) // 256) * 2
+    params = [p.detach() for p in net.kernel_params()]
+    dims = net._dims
+    cond = ops.fold_cond(dims, params, aud, expr, lat)
+    packed = net.packed_weights(net.kernel_params())
+    raw, acts, mask, _ = ops.mlp_fwd_train_bf16(dims, params, packed, cond, rays, z)
+    assert torch.equal(raw, ops.mlp_fwd(M._lib.INERF_MLP_BF16, dims, params, packed, cond, rays, z)), "saving build must not change raw"
+    g16, _ = ops.mlp_bwd_bf16(dims, params, net.packed_weights_bwd(net.kernel_params()), aud, expr, lat, acts, mask, G, P, keep_deltas=True)
+    A, D = ops.decode_images(acts, T), ops.decode_images(ops.mlp_bwd_bf16.deltas, T)
+    mw = mask.view(torch.int32).reshape(T, 76, 128)
+
+    def mask_bits(l):
+        w0, nw = (8 * l, 8) if l < 8 else (64 + 4 * (l - 8), 4)
+        words = mw[:, w0:w0 + nw].permute(0, 2, 1).reshape(-1, nw)
+        sh = 31 - torch.arange(32, device=DEV)
+        return ((words[:, :, None] >> sh[None, None, :]) & 1).reshape(-1, nw * 32).bool()
+
+    for l in range(11):
+        a16 = _img_cols(A, *_lay_img(l))[:P]
+        mb = mask_bits(l)[:P]
+        assert bool(mb[a16 > 0].all()), f"layer {l}: a positive activation without its mask bit"
+        extra = float((mb & (a16 == 0)).float().mean())      # mask = sign bit of the fp32 pre-activation: +0 / bf16-underflow keep the bit
+        print(f"[{n}x{s}] layer {l}: mask bits on zero activations: {extra:.2e}")
+        assert extra <= 1e-4, f"layer {l}: {extra}"
+    sdc = {k: v.to(DEV) for k, v in sd.items()}
+    C = 64 + 76 + 32
+    Gp = torch.zeros(T * 128, 4, device=DEV)
+    Gp[:P] = G.reshape(-1, 4)
+    d10 = torch.where(mask_bits(10), Gp[:, :3] @ sdc["rgb_linear.weight"], torch.zeros(1, device=DEV))
+    close(_img_cols(D, *_lay_img(10)), _bf(d10), 2.0 ** -7 * float(d10.abs().max()), "chain d_v2")
+    for l in range(10, 0, -1):
+        dl = _img_cols(D, *_lay_img(l))
+        W = sdc[f"pts_linears.{l}.weight"] if l < 8 else sdc[f"views_linears.{l - 8}.weight"]
+        Wa = W[:, :256] if l == 8 else (W[:, 63 + C:63 + C + 256] if l == 5 else W)
+        dh = dl @ _bf(Wa)
+        if l == 8:
+            dh = dh + Gp[:, 3:4] * sdc["alpha_linear.weight"]
+        ref = torch.where(mask_bits(l - 1), dh, torch.zeros(1, device=DEV))
+        got = _img_cols(D, *_lay_img(l - 1))
+        close(got, _bf(ref), 2.0 ** -7 * float(ref.abs().max()), f"chain delta of layer {l - 1}")
+        assert float(got[P:].abs().max()) == 0.0 if got.shape[0] > P else True, "rows past the last point must carry no gradient"
+
+    def chk(name, got, ref):
+        rel = float((got - ref).norm() / (ref.norm() + 1e-30))
+        assert rel <= 1e-4, (name, rel)
+
+    PE, DIR = _img_cols(A, 38, 1), _img_cols(A, 39, 1)
+    for l in range(11):
+        dl = _img_cols(D, *_lay_img(l))
+        wi = 2 * l if l < 8 else 16 + 2 * (l - 8)
+        if l == 0:
+            got, X = g16[0][:, :63], PE[:, :63]
+            assert float(g16[0][:, 63:].abs().max()) > 0.0           # conditioning columns: filled by the rank-1 kernel
+        elif l == 5:
+            got, X = torch.cat([g16[10][:, :63], g16[10][:, 63 + C:]], 1), torch.cat([PE[:, :63], _img_cols(A, *_lay_img(4))], 1)
+        elif l == 8:
+            got, X = g16[16][:, :283], torch.cat([_img_cols(A, *_lay_img(7)), DIR[:, :27]], 1)
+        else:
+            got, X = g16[wi], _img_cols(A, *_lay_img(l - 1))
+        chk(f"dW layer {l}", got, dl.T @ X)
+        chk(f"db layer {l}", g16[wi + 1], dl.sum(0))
+    dout = _img_cols(D, 38, 1)
+    chk("alpha weight", g16[22], dout[:, 3:4].T @ _img_cols(A, *_lay_img(7)))
+    chk("rgb weight", g16[24], dout[:, :3].T @ _img_cols(A, *_lay_img(10)))
+    chk("alpha bias", g16[23], dout[:, 3].sum(0, keepdim=True))
+    chk("rgb bias", g16[25], dout[:, :3].sum(0))
+
+
+@pytest.mark.parametrize("n,s", [(301, 64), (40, 192)])
+def test_bf16_training_grads(M, n, s):
+    """bf16 tensor-core training through autograd on (rays, z): against torch.autograd of an emulation that rounds where the kernel rounds,
+    and against the fp32 kernels.  Both yardsticks have slightly different pre-activations, so ~1e-3 of the ReLU masks flip and every flip
+    is an O(1) change of that delta entry: a few 1e-2 relative on a whole tensor is the floor of ANY such comparison (the tight check is
+    test_bf16_training_kernels_self_consistent)."""
+    b = O.synthetic_train_batch(0)
+    rays = b["rays"][:n].to(DEV)
+    sd = O.init_face_nerf(7)
+    n16, n32 = head_net(M, sd, "bf16"), head_net(M, sd, "fp32")
+    gen = torch.Generator(device=DEV).manual_seed(n)
+    z = M.ops.sample_coarse(rays, s, torch.rand(n, s, device=DEV, generator=gen))
+    G = torch.randn(n, s, 4, device=DEV, generator=gen) * torch.tensor([1., 1., 1., 0.3], device=DEV)
+    grads = {}
+    for tag, net in (("bf16", n16), ("fp32", n32)):
+        aud, expr, lat = (b[k].to(DEV).clone().requires_grad_(True) for k in ("aud", "expr", "latent"))
+        raw = net.query(rays, z, aud, expr, lat)
+        (raw * G).sum().backward()
+        grads[tag] = ({k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}, aud.grad, expr.grad, lat.grad, raw.detach())
+    sdg = {k: v.to(DEV).clone().requires_grad_(True) for k, v in sd.items()}
+    aud, expr, lat = (b[k].to(DEV).clone().requires_grad_(True) for k in ("aud", "expr", "latent"))
+    pts = (rays[:, None, 0:3] + rays[:, None, 3:6] * z[..., None]).reshape(-1, 3)
+    e10, _ = M.get_embedder(10, 0); e4, _ = M.get_embedder(4, 0)
+    with torch.no_grad():
+        pe, de = e10(pts), e4(rays[:, None, 8:11].expand(n, s, 3).reshape(-1, 3))
+    raw_e = _emulated_bf16_forward(sdg, pe, de, aud, expr, lat).reshape(n, s, 4)
+    (raw_e * G).sum().backward()
+    close(grads["bf16"][4], raw_e, 6e-3 * max(1.0, float(raw_e.abs().max())), "bf16 training forward vs emulation")
+    for k, gk in grads["bf16"][0].items():
+        ref, r32 = sdg[k].grad, grads["fp32"][0][k]
+        if float(r32.abs().max()) == 0.0:
+            continue
+        rel = float((gk - ref).norm() / ref.norm())
+        cos = float(torch.nn.functional.cosine_similarity(gk.flatten().double(), r32.flatten().double(), dim=0))
+        print(f"[{n}x{s}] {k:26s} rel-L2 vs emulation {rel:.3e}   cos vs fp32 kernels {cos:.5f}")
+        assert rel <= 0.1, (k, rel)
+        assert cos >= 0.97, (k, cos)
+    for i, nm in ((1, "d_aud"), (2, "d_expr"), (3, "d_latent")):
+        ref = (aud, expr, lat)[i - 1].grad
+        rel = float((grads["bf16"][i] - ref).norm() / ref.norm())
+        print(f"[{n}x{s}] {nm}: rel-L2 vs emulation {rel:.3e}")
+        assert rel <= 0.1, (nm, rel)
+
+
+def test_bf16_training_loop_reduces_loss(M):
+    """The config-3 step in bf16 mode: a few Adam steps on a fixed 256-ray batch must reduce the loss like the fp32 path does."""
+    b = O.synthetic_train_batch(0)
+    idx = torch.arange(0, 3072, 12)
+    losses = {}
+    for mode in ("bf16", "fp32"):
+        args = M.default_args(dim_aud=64, dim_expr=76, perturb=0.0, N_samples=64, N_importance=128, mlp_mode=mode)
+        net = M.Network(450, 450, 1200., O.NEAR, O.FAR, 8192, None, 64, 128, args=args)
+        torch.manual_seed(0)
+        net.apply(M.init_weights)
+        net = net.to(DEV).train()
+        lat = torch.ones(32, device=DEV, requires_grad=True)
+        opt = torch.optim.Adam(list(net.parameters()) + [lat], lr=3e-3, betas=(0.9, 0.999))
+        rays, bc, tgt = b["rays"][idx].to(DEV), b["bc_rgb"][idx].to(DEV), b["target"][idx].to(DEV)
+        aud, expr = b["aud"].to(DEV), b["expr"].to(DEV)
+        ls = []
+        for _ in range(6):
+            opt.zero_grad()
+            r = net.render_rays(rays, bc, aud, None, lat, expr)
+            loss = torch.mean((r["rgb_map"] - tgt) ** 2) + torch.mean((r["rgb0"] - tgt) ** 2) + 10 * 0.0005 * torch.norm(lat)
+            loss.backward()
+            opt.step()
+            ls.append(float(loss.detach()))
+        losses[mode] = ls
+    print("losses", losses)
+    assert losses["bf16"][-1] < losses["bf16"][0] and all(np.isfinite(losses["bf16"]))
+    assert abs(losses["bf16"][-1] - losses["fp32"][-1]) <= 0.05 * abs(losses["fp32"][0]), "bf16 and fp32 training must track each other"
