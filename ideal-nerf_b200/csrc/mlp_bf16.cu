@@ -447,22 +447,13 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                                 case 10: epi_convert<3, TRACE, SAVE>(r, &packed[c * 16], nullptr, nullptr, s_rw + f0, alpha, rgb0, rgb1, rgb2, tr, dump, neg); break;
                                 default: epi_convert<0, TRACE, SAVE>(r, &packed[c * 16], nullptr, nullptr, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump, neg); break;
                             }
-                            if constexpr (SAVE) {
-                                // training: the chunk as it goes to shared memory (same swizzled image, 4 x 16 B) + its ReLU mask word
-                                const size_t T = (size_t)it * 2 + slot;
-                                uint8_t* img = a.save_img + (T * TRAIN_IMGS + train_img_of(l) + (f0 >> 6)) * 16384 + row_off;
-                                const int ch0 = (f0 & 63) >> 3;
-#pragma unroll
-                                for (int q = 0; q < 4; ++q)
-                                    *reinterpret_cast<uint4*>(img + (((ch0 + q) ^ rsw) << 4)) =
-                                        make_uint4(packed[c * 16 + q * 4], packed[c * 16 + q * 4 + 1], packed[c * 16 + q * 4 + 2], packed[c * 16 + q * 4 + 3]);
-                                a.save_mask[(T * TRAIN_MASK_WORDS + train_mask_of(l) + (f0 >> 5)) * 128 + row] = ~neg;
-                            }
+                            if constexpr (SAVE)      // training: the ReLU mask word of the chunk (the activations follow as a bulk copy of the smem image)
+                                a.save_mask[(((size_t)it * 2 + slot) * TRAIN_MASK_WORDS + train_mask_of(l) + (f0 >> 5)) * 128 + row] = ~neg;
                         }
                     }
                     tc_fence_before();
                     if constexpr (TRACE) { const long long q1 = clock64(); te_ld += q1 - q0; q0 = q1; }
-                    if (l != 10) {
+                    if (l != 10 || SAVE) {
                         if (h == 0) wait_or_report<TRACE>(&bars->cbar[1], par, 304, l, (int)layer_ctr);
                         __syncwarp();      // h1 has finished reading the K-blocks written below
                         if constexpr (TRACE) { const long long q1 = clock64(); te_c1 += q1 - q0; q0 = q1; }
@@ -481,6 +472,20 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                             }
                         }
                         fence_proxy_async_smem();
+                        if constexpr (SAVE) {
+                            // training: the K-blocks this half just wrote go to HBM as ONE bulk copy of their shared-memory image, issued
+                            // by thread 1 of the slot.  It first waits until its previous copy (the other half's K-blocks) has been read
+                            // out of shared memory, so whoever passes this barrier may overwrite those K-blocks again.
+                            const bool issuer = (row == 1);
+                            if (issuer) bulk_wait_read_all();
+                            named_bar_sync(1 + slot, 128);
+                            if (issuer) {
+                                const int f0h = h * NH;
+                                bulk_s2g(a.save_img + (((size_t)it * 2 + slot) * TRAIN_IMGS + train_img_of(l) + (f0h >> 6)) * 16384,
+                                         act + (f0h >> 6) * 16384, (uint32_t)NH * 256u);      // NH columns = NH/64 K-block images of 16 KB
+                                bulk_commit();
+                            }
+                        }
                     }
                     // one arrival per warp: 256 per-thread arrivals on one mbarrier serialise in the shared-memory pipe and sit on
                     // the layer-to-layer critical path (E1 gates the next layer's third K-block)
@@ -501,6 +506,9 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                 o.w = alpha + s_sb[0];
                 reinterpret_cast<float4*>(a.out)[p] = o;
             }
+        }
+        if constexpr (SAVE) {
+            if (row == 1) bulk_wait_all();
         }
         if constexpr (TRACE) {
             if (warp == 4 && lane == 0) {

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(NTH, 1) mlp_bf16_bwd_chain_kernel(BwdChainArgs
                 const uint32_t* mp = a.mask + (T * TRAIN_MASK_WORDS + train_mask_of(lo)) * 128 + row;
 #pragma unroll
                 for (int w = 0; w < 8; ++w) mw[w] = (w < (N >> 5)) ? __ldg(mp + w * 128) : 0u;
-                uint8_t* gimg = a.delta_img + (T * TRAIN_IMGS + train_img_of(lo)) * 16384 + row_off;
+                uint8_t* gimg_base = a.delta_img + (T * TRAIN_IMGS + train_img_of(lo)) * 16384;
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
                     bwait(&bars->cbar[h == 0 ? 0 : 2], par);
@@ -242,7 +242,6 @@ __global__ void __launch_bounds__(NTH, 1) mlp_bf16_bwd_chain_kernel(BwdChainArgs
                             uint32_t r[32];
                             tmem_ld32(t_lane + h * NH + c * 32, r);
                             tmem_wait_ld();
-                            const int f0 = h * NH + c * 32;
                             const uint32_t m = (h == 0) ? mw[c] : (NH == 128 ? mw[4 + c] : mw[2 + c]);      // word f0 / 32
 #pragma unroll
                             for (int q = 0; q < 16; ++q) {
@@ -250,17 +249,22 @@ __global__ void __launch_bounds__(NTH, 1) mlp_bf16_bwd_chain_kernel(BwdChainArgs
                                 const float v1 = (m & (0x80000000u >> (2 * q + 1))) ? __uint_as_float(r[2 * q + 1]) : 0.f;
                                 packed[c * 16 + q] = pack_bf16x2(v0, v1);
                             }
-                            // the delta image for dW (same swizzled layout as shared memory)
-                            const int ch0 = (f0 & 63) >> 3;
-                            uint8_t* gk = gimg + (f0 >> 6) * 16384;
+                        }
+                    }
+                    tc_fence_before();
+                    if (j == NLAY - 1) {
+                        // d_h0 feeds no further GEMM: straight to HBM (the init warps of the next iteration may already be refilling the
+                        // shared-memory K-blocks, so they are not used as a staging buffer here)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int f0 = h * NH + c * 32, ch0 = (f0 & 63) >> 3;
+                            uint8_t* gk = gimg_base + (f0 >> 6) * 16384 + row_off;
 #pragma unroll
                             for (int q = 0; q < 4; ++q)
                                 *reinterpret_cast<uint4*>(gk + (((ch0 + q) ^ rsw) << 4)) =
                                     make_uint4(packed[c * 16 + q * 4], packed[c * 16 + q * 4 + 1], packed[c * 16 + q * 4 + 2], packed[c * 16 + q * 4 + 3]);
                         }
-                    }
-                    tc_fence_before();
-                    if (j != NLAY - 1) {
+                    } else {
                         if (h == 0) bwait(&bars->cbar[1], par);
                         __syncwarp();
 #pragma unroll
@@ -276,12 +280,23 @@ __global__ void __launch_bounds__(NTH, 1) mlp_bf16_bwd_chain_kernel(BwdChainArgs
                             }
                         }
                         fence_proxy_async_smem();
+                        // the delta image for dW: ONE bulk copy of the K-blocks this half just wrote (their shared-memory image), issued by
+                        // thread 1 of the slot once its previous copy has been read out (so those K-blocks may be overwritten again)
+                        const bool issuer = (row == 1);
+                        if (issuer) bulk_wait_read_all();
+                        named_bar_sync(1 + slot, 128);
+                        if (issuer) {
+                            const int f0h = h * NH;
+                            bulk_s2g(gimg_base + (f0h >> 6) * 16384, act + (f0h >> 6) * 16384, (uint32_t)NH * 256u);      // NH columns = NH/64 K-block images of 16 KB
+                            bulk_commit();
+                        }
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->ebar[h]);
                 }
             }
         }
+        if (row == 1) bulk_wait_all();
     } else if (warp >= 12) {
         // ================= init: d_raw -> d_v2, d_sigma tile, d_raw image ==================================================
         // Phase 1 (any time): d_v2 and the d_raw image of row t of both slots go to HBM (the dW kernel needs them there anyway).

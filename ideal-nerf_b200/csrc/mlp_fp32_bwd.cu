@@ -318,7 +318,7 @@ __global__ void mlp_bwd_cond_kernel(CondBwdArgs c) {
     for (int j = threadIdx.x; j < nj; j += blockDim.x) {
         float dc = 0.f;
         const float cj = cv[j0 + j];
-        for (int n = 0; n < N; ++n) {
+        for (int n = blockIdx.y * (N / gridDim.y); n < (int)(blockIdx.y + 1) * (N / (int)gridDim.y); ++n) {      // gridDim.y slices of the rows
             const float db = c.gb[job][n];
             dc = fmaf(c.w[job][(size_t)n * ldw + col0 + j], db, dc);
             c.gw[job][(size_t)n * ldw + col0 + j] = db * cj;     // rank-1: these columns see the same input at every point
@@ -409,7 +409,7 @@ int mlp_bwd_cond_launch(const InerfNetDims* dims, const float* const* params_hos
     c.gb[0] = grads_host[1]; c.gb[1] = grads_host[11]; c.gb[2] = grads_host[P_VIEWS_W + 1];
     c.aud = aud; c.expr = expr; c.latent = latent;
     c.da = dims->dim_aud; c.de = E; c.dl = dims->dim_latent; c.d_cond = d_cond;
-    mlp_bwd_cond_kernel<<<E > 0 ? 3 : 2, 256, 0, st>>>(c);
+    mlp_bwd_cond_kernel<<<dim3(E > 0 ? 3 : 2, 16), 256, 0, st>>>(c);
     return check_launch("inerf_mlp_bwd[cond]");
 }
 

@@ -55,3 +55,21 @@ class FrameRenderer:
     def render_frame(self, pose, aud, expr, latent, bc_rgb, perturb=0.):
         ret, _ = self.render_band(pose, aud, expr, latent, bc_rgb, perturb)
         return self.gather_image(ret['rgb_map'], self.net.H * self.net.W)
+
+
+def allreduce_grads(parameters, world, group=None):
+    """Data-parallel training step, the reference's nn.DataParallel backward (distribute_nerf.py:423) as one process per GPU: every rank
+    ran render_rays + loss.backward() on its band of the N_rand rays (band(N_rand, rank, world)); the gradients of all parameters are
+    flattened into ONE buffer, summed with a single NCCL all-reduce (~6 MB over NVLink) and divided by `world`, so that mean-over-rays
+    losses reproduce the single-process gradient when the bands have equal size.  Parameters without a gradient are skipped."""
+    ps = [p for p in parameters if p.grad is not None]
+    if world == 1 or not ps:
+        return
+    flat = torch.cat([p.grad.reshape(-1) for p in ps])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(world)
+    o = 0
+    for p in ps:
+        n = p.grad.numel()
+        p.grad.copy_(flat[o:o + n].view_as(p.grad))
+        o += n

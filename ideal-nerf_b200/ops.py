@@ -256,6 +256,18 @@ def importance_sample(z_coarse, w_coarse, u, policy=_lib.INERF_PDF_EXACT_TORCH_C
 # FaceNeRF MLP
 # ------------------------------------------------------------------------------------------------
 
+def zero_grads_like(params):
+    """Zero gradient tensors for `params` as views of ONE flat buffer (a single memset instead of 26 fill kernels; the flat
+    buffer is what a data-parallel all-reduce sends).  Returns (views, flat)."""
+    sizes = [(p.numel() + 3) // 4 * 4 for p in params]                 # 16-byte aligned starts
+    flat = torch.zeros((sum(sizes),), device=params[0].device, dtype=torch.float32)
+    views, o = [], 0
+    for p, n in zip(params, sizes):
+        views.append(flat[o:o + p.numel()].view(p.shape))
+        o += n
+    return views, flat
+
+
 def net_dims(dim_aud, dim_expr, dim_latent):
     return InerfNetDims(int(dim_aud), int(dim_expr), int(dim_latent), 256, 8, 63, 27)
 
@@ -339,7 +351,7 @@ def mlp_bwd(dims, params, aud, expr, latent, acts, d_raw, n_points):
     check(_lib.lib().inerf_mlp_train_sizes(ctypes.byref(dims), n_points, *[ctypes.byref(v) for v in sizes]), "inerf_mlp_train_sizes")
     deltas = torch.empty((sizes[1].value,), device=dev)
     scratch = torch.empty((sizes[2].value,), device=dev, dtype=torch.uint8)
-    grads = [torch.zeros_like(p) for p in params]
+    grads, _ = zero_grads_like(params)
     d_cond = torch.zeros((max(1, dims.dim_aud + dims.dim_expr + dims.dim_latent),), device=dev)
     d_raw = f32c(d_raw, "d_raw").reshape(-1, 4)
     parr, garr = param_array(params), param_array(grads)
@@ -377,7 +389,7 @@ def mlp_bwd_bf16(dims, params, packed_t, aud, expr, latent, acts, mask, d_raw, n
     _, _, deltas_b, scratch_b = _train_sizes_bf16(dims, n_points)
     deltas = torch.empty((deltas_b,), device=dev, dtype=torch.uint8)
     scratch = torch.empty((scratch_b,), device=dev, dtype=torch.uint8)
-    grads = [torch.zeros_like(p) for p in params]
+    grads, _ = zero_grads_like(params)
     d_cond = torch.zeros((max(1, dims.dim_aud + dims.dim_expr + dims.dim_latent),), device=dev)
     d_raw = f32c(d_raw, "d_raw").reshape(-1, 4)
     parr, garr = param_array(params), param_array(grads)

@@ -58,3 +58,35 @@ def test_gather_image_world2_gloo():
         shape, ok = q.get(timeout=10)
         assert shape == (n_rays, 3) and ok
         port = _free_port()
+
+
+def _train_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ideal_nerf_b200.frame import allreduce_grads, band
+    torch.manual_seed(0)                                   # identical replica on every rank
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3))
+    x, y = torch.randn(3072, 5), torch.randn(3072, 3)      # the N_rand batch
+    lo, hi = band(3072, rank, world)
+    torch.mean((net(x[lo:hi]) - y[lo:hi]) ** 2).backward()
+    allreduce_grads(net.parameters(), world)
+    if rank == 0:
+        ref = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3))
+        ref.load_state_dict(net.state_dict())
+        torch.mean((ref(x) - y) ** 2).backward()
+        q.put(max(float((a.grad - b.grad).abs().max()) for a, b in zip(net.parameters(), ref.parameters())))
+    dist.destroy_process_group()
+
+
+def test_allreduce_grads_world2_gloo_matches_full_batch():
+    """Training rays sharded over 2 ranks + one flat gradient all-reduce == the single-process gradient (mean loss, equal bands)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) <= 1e-6
