@@ -38,7 +38,8 @@ struct PdfArgs {
     float* z_samples; long long* inds;
     const float* z_coarse; int s1;
     float* z_merged; float* z_std;
-    int sort_n;        // power of two >= s1 + n_imp (0 when no merge)
+    int sort_n;        // shared floats of the merge (0 when no merge): s1 + imp_p2 + s1 + n_imp
+    int imp_p2;        // power of two >= n_imp
     int warp_floats;   // shared floats per warp
 };
 
@@ -145,25 +146,46 @@ __global__ void __launch_bounds__(256) sample_pdf_kernel(PdfArgs a) {
     }
 
     if (a.sort_n) {                             // z_vals = sort(cat([z_vals, z_samples]))  (:347)
-        const int tot = a.s1 + a.n_imp, P = a.sort_n;
+        // The coarse depths are already sorted; the samples are sorted when u is (the shared linspace table of det=True: the
+        // inverse CDF is monotone), otherwise a bitonic sort of the n_imp samples alone.  Then a rank merge: every element's
+        // output slot is its own index plus the number of elements of the OTHER list that precede it (strict for the coarse
+        // list, non-strict for the samples, so ties get distinct slots) -- 7-step binary searches instead of sorting s1+n_imp.
+        const int tot = a.s1 + a.n_imp, P2 = a.imp_p2;
+        float* zsm = ssm + a.s1;                // [P2] samples (padded with +inf)
+        float* osm = zsm + P2;                  // [tot] merged row
         const float* zc = a.z_coarse + (size_t)ray * a.s1;
         for (int j = lane; j < a.s1; j += 32) ssm[j] = zc[j];
-        for (int j = tot + lane; j < P; j += 32) ssm[j] = CUDART_INF_F;
+        for (int j = a.n_imp + lane; j < P2; j += 32) zsm[j] = CUDART_INF_F;
         __syncwarp();
-        for (int k = 2; k <= P; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int t = lane; t < (P >> 1); t += 32) {
-                    int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                    int p = i | j;
-                    float x = ssm[i], y = ssm[p];
-                    bool up = (i & k) == 0;
-                    if ((x > y) == up) { ssm[i] = y; ssm[p] = x; }
+        if (a.u_per_ray) {
+            for (int k = 2; k <= P2; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = lane; t < (P2 >> 1); t += 32) {
+                        int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                        int p = i | j;
+                        float x = zsm[i], y = zsm[p];
+                        bool up = (i & k) == 0;
+                        if ((x > y) == up) { zsm[i] = y; zsm[p] = x; }
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
+        for (int j = lane; j < a.s1; j += 32) {             // coarse j: samples strictly below it come first
+            const float v = ssm[j];
+            int lo = 0, hi = a.n_imp;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (zsm[mid] < v) lo = mid + 1; else hi = mid; }
+            osm[j + lo] = v;
+        }
+        for (int i = lane; i < a.n_imp; i += 32) {          // sample i: coarse depths <= it come first
+            const float v = zsm[i];
+            int lo = 0, hi = a.s1;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (ssm[mid] <= v) lo = mid + 1; else hi = mid; }
+            osm[i + lo] = v;
+        }
+        __syncwarp();
         float* out = a.z_merged + (size_t)ray * tot;
-        for (int j = lane; j < tot; j += 32) out[j] = ssm[j];
+        for (int j = lane; j < tot; j += 32) out[j] = osm[j];
     }
 }
 
@@ -178,8 +200,9 @@ int launch_pdf(PdfArgs a, void* stream) {
     if (a.z_merged) {
         if (!a.z_coarse || a.s1 <= 0 || a.s1 + a.n_imp > 2048) return fail(INERF_E_SHAPE, "sample_pdf: merge needs z_coarse and s1+n_imp <= 2048");
         int p = 2;
-        while (p < a.s1 + a.n_imp) p <<= 1;
-        a.sort_n = p;
+        while (p < a.n_imp) p <<= 1;
+        a.imp_p2 = p;
+        a.sort_n = a.s1 + p + a.s1 + a.n_imp;
     }
     int nw = a.nb - 1;
     a.warp_floats = ((nw + 3) & ~3) + 2 * ((a.nb + 3) & ~3) + a.sort_n;
