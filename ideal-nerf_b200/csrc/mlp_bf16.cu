@@ -762,6 +762,16 @@ int mlp_bf16_pack(const InerfNetDims* d, const float* const* params_host, void* 
     return check_launch("inerf_mlp_pack");
 }
 
+void mlp_bf16_stage_offsets(uint32_t (*off)[2][5]) {
+    InerfNetDims d{64, 76, 32, 256, 8, 63, 27};              // offsets do not depend on the conditioning dims
+    Schedule S = build_schedule(&d);
+    int idx[11][2] = {};
+    for (int n = 0; n < S.n_steps; ++n) {
+        const int l = S.steps[n].layer, h = S.steps[n].acc_col ? 1 : 0;
+        off[l][h][idx[l][h]++] = S.steps[n].offset;
+    }
+}
+
 static int* g_hang_host = nullptr;
 
 int mlp_bf16_hang_info(int32_t* out8) {
@@ -813,6 +823,7 @@ int mlp_bf16_launch(const MlpArgs& a, bool embedded, cudaStream_t st) {
         if (abl >= 1 && abl <= 24) return check_launch("inerf_mlp_fwd[bf16,ablation]");
     }
 #endif
+    if (!a.save_img && getenv("INERF_MLP_V2")) return mlp_bf16_v2_launch(a, st);      // a.trace: v2 writes phase timings there
     if (a.save_img) {
         if (!a.save_mask) return fail(INERF_E_ARG, "mlp_bf16: save_mask is NULL");
         static thread_local int save_dev = -1;

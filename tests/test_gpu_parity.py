@@ -8,6 +8,8 @@ Tolerances (BASELINE.json north_star):
   * fp32 MLP mode: rgb / depth / acc max-abs <= 1e-3 end to end (measured ~1e-5; asserted at 1e-4
     where the golden comparison allows it);
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -759,3 +761,27 @@ def test_bf16_training_loop_reduces_loss(M):
     print("losses", losses)
     assert losses["bf16"][-1] < losses["bf16"][0] and all(np.isfinite(losses["bf16"]))
     assert abs(losses["bf16"][-1] - losses["fp32"][-1]) <= 0.05 * abs(losses["fp32"][0]), "bf16 and fp32 training must track each other"
+
+
+@pytest.mark.parametrize("n,s", [(8, 64), (301, 64), (47, 45), (333, 192)])
+def test_bf16_pair_kernel_v2_bit_matches_v1(M, n, s):
+    """The experimental cta_group::2 kernel (csrc/mlp_bf16_v2.cu, INERF_MLP_V2=1: CTA pairs, M = 256 MMAs over the whole layer width,
+    slots alternating, remote mbarrier arrivals) reads the same packed blob and bias tiles and must return the same bits as v1,
+    including chunks past the end of a ragged input (one CTA of the last pair idles on clamped points)."""
+    b = O.synthetic_train_batch(0)
+    rays = b["rays"][:n].to(DEV)
+    net = head_net(M, O.init_face_nerf(7), "bf16")
+    aud, expr, lat = b["aud"].to(DEV), b["expr"].to(DEV), b["latent"].to(DEV)
+    z = M.ops.sample_coarse(rays, s, torch.rand(n, s, device=DEV, generator=torch.Generator(device=DEV).manual_seed(s)))
+    old = os.environ.pop("INERF_MLP_V2", None)
+    try:
+        with torch.no_grad():
+            r1 = net.query(rays, z, aud, expr, lat)
+            os.environ["INERF_MLP_V2"] = "1"
+            r2 = net.query(rays, z, aud, expr, lat)
+    finally:
+        os.environ.pop("INERF_MLP_V2", None)
+        if old is not None:
+            os.environ["INERF_MLP_V2"] = old
+    assert torch.isfinite(r2).all()
+    assert torch.equal(r1, r2)
