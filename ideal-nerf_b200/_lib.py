@@ -46,6 +46,7 @@ SIGNATURES = {
     "inerf_get_rays": (_I, [_I, _I, _F, _F, _F, _P, _I, _F, _F, _P, _P]),
     "inerf_pack_rays": (_I, [_P, _P, _I, _F, _F, _P, _P]),
     "inerf_posenc": (_I, [_P, _L, _I, _I, _P, _P]),
+    "inerf_to8b": (_I, [_P, _L, _P, _P]),
     "inerf_sample_coarse": (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P]),
     "inerf_composite_fwd": (_I, [_P, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "inerf_composite_bwd": (_I, [_P, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -163,3 +163,31 @@ extern "C" int inerf_head_torso_blend(const float* rgb_head, const float* last_w
     blend_kernel<<<(n * 3 + 255) / 256, 256, 0, as_stream(stream)>>>(rgb_head, last_weight_torso, rgb_fg_torso, n, rgb);
     return check_launch("inerf_head_torso_blend");
 }
+
+// ---------------------------------------------------------------------------------------------
+// to8b: (255 * clip(x, 0, 1)).astype(uint8)   helper.py:154 (used on every rendered frame, eval_aud_exp_nerf.py:490)
+// ---------------------------------------------------------------------------------------------
+__global__ void to8b_kernel(const float* __restrict__ x, long long n, uint8_t* __restrict__ out) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    if (i + 3 < n && ((uintptr_t)(x + i) & 15) == 0 && ((uintptr_t)(out + i) & 3) == 0) {
+        const float4 v = *reinterpret_cast<const float4*>(x + i);
+        uchar4 o;
+        o.x = (uint8_t)(int)__fmul_rn(255.f, fminf(fmaxf(v.x, 0.f), 1.f));      // float -> int truncates like astype
+        o.y = (uint8_t)(int)__fmul_rn(255.f, fminf(fmaxf(v.y, 0.f), 1.f));
+        o.z = (uint8_t)(int)__fmul_rn(255.f, fminf(fmaxf(v.z, 0.f), 1.f));
+        o.w = (uint8_t)(int)__fmul_rn(255.f, fminf(fmaxf(v.w, 0.f), 1.f));
+        *reinterpret_cast<uchar4*>(out + i) = o;
+    } else {
+        for (long long j = i; j < n && j < i + 4; ++j) out[j] = (uint8_t)(int)__fmul_rn(255.f, fminf(fmaxf(x[j], 0.f), 1.f));
+    }
+}
+
+extern "C" int inerf_to8b(const float* x, int64_t n, uint8_t* out, void* stream) {
+    if (n < 0) return fail(INERF_E_SHAPE, "inerf_to8b: n < 0");
+    if (n == 0) return INERF_OK;
+    if (!x || !out) return fail(INERF_E_ARG, "inerf_to8b: NULL pointer");
+    const long long threads = (n + 3) / 4;
+    to8b_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, as_stream(stream)>>>(x, n, out);
+    return check_launch("inerf_to8b");
+}

@@ -135,3 +135,9 @@ def sample_pdf(bins, weights, N_samples, det=False, pytest=False, policy=_lib.IN
         u = torch.rand((n, N_samples), device=dev)
     samples, _ = ops.sample_pdf_raw(bins, weights, u, policy)
     return samples
+
+
+def to8b(x):
+    """helper.py:154 ``(255 * np.clip(x, 0, 1)).astype(np.uint8)`` for a CUDA tensor: returns a uint8 CUDA tensor of the same shape
+    (one kernel; the frame then leaves the GPU as bytes)."""
+    return ops.to8b(x)

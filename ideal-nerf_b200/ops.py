@@ -114,6 +114,15 @@ def posenc(x, n_freqs):
     return out.reshape(*x.shape[:-1], out.shape[-1])
 
 
+def to8b(x):
+    """(255 * clip(x, 0, 1)).astype(uint8) on the device (helper.py:154)."""
+    x = f32c(x, "x")
+    out = torch.empty(x.shape, device=x.device, dtype=torch.uint8)
+    with torch.cuda.device(x.device):
+        call("inerf_to8b", _lib.lib().inerf_to8b, ptr(x), x.numel(), ptr(out), stream())
+    return out
+
+
 def sample_coarse(rays, n_samples, t_rand=None, lindisp=False):
     rays = f32c(rays, "rays")
     n = rays.shape[0]

@@ -95,6 +95,10 @@ int inerf_pack_rays(const float* rays_o, const float* rays_d, int n, float near_
  * Replaces helper.py:174-224 (Embedder.embed via get_embedder).  x: (n, dims), out: (n, dims*(1+2L)). */
 int inerf_posenc(const float* x, int64_t n, int dims, int n_freqs, float* out, void* stream);
 
+/* to8b(x) = (255 * clip(x, 0, 1)).astype(uint8).  Replaces helper.py:154 on the rendered frame (eval_aud_exp_nerf.py:490,
+ * test_torso.py:524): the image leaves the GPU as n bytes instead of 4n.  x: n floats; out: n bytes. */
+int inerf_to8b(const float* x, int64_t n, uint8_t* out, void* stream);
+
 /* Stratified coarse depths.  Replaces audio_exp_nerf.py:306-328 (baseline.py:385-410).
  * rays: (n, ray_stride) with near/far in columns 6,7.  t_vals: (s) = torch.linspace(0,1,s) (a host
  * generated table -- SURVEY.md 7-1).  t_rand: NULL (perturb == 0) or (n, s) uniform draws; the last

@@ -785,3 +785,31 @@ def test_bf16_pair_kernel_v2_bit_matches_v1(M, n, s):
             os.environ["INERF_MLP_V2"] = old
     assert torch.isfinite(r2).all()
     assert torch.equal(r1, r2)
+
+
+def test_to8b_and_video_driver(M):
+    """to8b bit-for-bit against numpy (helper.py:154, incl. out-of-range / NaN-free edge values and a ragged length), and the video
+    driver: frames rendered, converted on the device and copied asynchronously == to8b(render_dynamic_face) frame by frame."""
+    gen = torch.Generator().manual_seed(3)
+    x = torch.cat([torch.rand(1001, generator=gen) * 1.4 - 0.2, torch.tensor([0., 1., 0.5, 1. / 255, 254.9999 / 255, -0.0, 2.0])])
+    ref = (255 * np.clip(x.numpy(), 0, 1)).astype(np.uint8)
+    assert np.array_equal(M.to8b(x.to(DEV)).cpu().numpy(), ref)
+    assert M.to8b(torch.zeros(0, device=DEV)).shape == (0,)
+    from ideal_nerf_b200.frame import FrameRenderer, render_video
+    from ideal_nerf_b200 import synthetic as S
+    cam = S.camera()
+    args = M.default_args(dim_aud=64, dim_expr=76, perturb=0., mlp_mode="bf16", N_samples=64, N_importance=128, near=S.NEAR, far=S.FAR)
+    net = M.Network(30, 40, cam["focal"] * 40 / 450, S.NEAR, S.FAR, 1 << 20, None, 64, 128, args=args)
+    torch.manual_seed(5)
+    net.apply(M.init_weights)
+    net = net.to(DEV).eval()
+    frs = [S.frame_inputs(i) for i in range(3)]
+    bc = torch.rand(30 * 40, 3, generator=gen).to(DEV)
+    lat = frs[0]["latent"].to(DEV)
+    frames = [(f["pose"].to(DEV), f["aud"].to(DEV), f["expr"].to(DEV)) for f in frs]
+    with torch.no_grad():
+        vid = render_video(FrameRenderer(net), frames, lat, bc)
+        assert vid.shape == (3, 30, 40, 3) and vid.dtype == torch.uint8
+        for i, (pose, aud, expr) in enumerate(frames):
+            rgb = FrameRenderer(net).render_frame(pose, aud, expr, lat, bc)
+            assert np.array_equal(vid[i].numpy().reshape(-1, 3), (255 * np.clip(rgb.cpu().numpy(), 0, 1)).astype(np.uint8))
