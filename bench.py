@@ -146,6 +146,32 @@ def build_network(mode, dev):
     return M, net, fr, cam
 
 
+def composite_standalone(M, dev, n_rays, reps=20):
+    """raw2outputs alone on frame-sized resident tensors (S = 64 then S = 192), `reps` back-to-back launches per CUDA-event pair:
+    the inputs of one launch (207 / 622 MB of raw) exceed L2, so every launch streams from HBM, and the per-launch event overhead
+    that dominates the in-step figure (0.1 ms kernels) is amortised.  Returns (algorithmic bytes, ms) summed over both shapes."""
+    from ideal_nerf_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(11)
+    tot_bytes, tot_ms = 0.0, 0.0
+    d = torch.randn(n_rays, 3, device=dev, generator=g)
+    bc = torch.rand(n_rays, 3, device=dev, generator=g)
+    for s in (S1, S1 + S_IMP):
+        raw = torch.randn(n_rays, s, 4, device=dev, generator=g)
+        z = torch.sort(torch.rand(n_rays, s, device=dev, generator=g), -1)[0]
+        for _ in range(3):
+            ops.composite(raw, z, d, bc)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            ops.composite(raw, z, d, bc)
+        e1.record()
+        torch.cuda.synchronize()
+        tot_ms += e0.elapsed_time(e1) / reps
+        tot_bytes += n_rays * (24 * s + 48)
+    return tot_bytes, tot_ms
+
+
 def train_step_bench(M, dev, steps, mode="bf16"):
     """BASELINE.json config 3: N_rand=3072 rays (64+128 samples), loss of audio_exp_nerf.py:540-548, backward through
     compositing + both FaceNeRFs, Adam(lr=3e-4) step.  mode: bf16 = tcgen05 forward-with-save + chain + dW kernels; fp32 = FFMA."""
@@ -289,6 +315,8 @@ def run_ours(args):
         peak = pk["bf16_tflops_sustained"]
         n_cmp, cmp_ms = ksum.get("inerf_composite_fwd", (0, 0.0))
         cmp_bytes = (hi - lo) * frames * args.steps * ((24 * S1 + 48) + (24 * (S1 + S_IMP) + 48))
+        with torch.no_grad():
+            sa_bytes, sa_ms = composite_standalone(M, dev, hi - lo)
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -306,10 +334,11 @@ def run_ours(args):
                          "peak_kind": f"bf16 dense sustained, {pk_kind}", "launches": n_mlp, "kernel_ms_total": mlp_ms,
                          "share_of_step": mlp_ms / total_ms if total_ms else None},
             "roofline_composite": {"bound": "hbm", "kernel": "inerf_composite_fwd",
-                                   "achieved": cmp_bytes / (cmp_ms * 1e-3) / 1e9 if cmp_ms > 0 else None,
-                                   "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                   "frac": (cmp_bytes / (cmp_ms * 1e-3) / 1e9 / pk["hbm_gbs"]) if cmp_ms > 0 else None,
-                                   "launches": n_cmp, "kernel_ms_total": cmp_ms},
+                                   "achieved": sa_bytes / (sa_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                   "frac": sa_bytes / (sa_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                   "how": "stand-alone, 20 back-to-back launches per event pair on frame-sized resident inputs (S=64 and S=192)",
+                                   "in_step": {"achieved": cmp_bytes / (cmp_ms * 1e-3) / 1e9 if cmp_ms > 0 else None, "launches": n_cmp,
+                                               "kernel_ms_total": cmp_ms, "note": "one event pair per 0.1 ms launch: includes event overhead"}},
             "kernels_ms": {k: round(v[1], 3) for k, v in ksum.items()},
         }
         if world == 1 and not args.no_train:

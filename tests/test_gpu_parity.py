@@ -813,3 +813,42 @@ def test_to8b_and_video_driver(M):
         for i, (pose, aud, expr) in enumerate(frames):
             rgb = FrameRenderer(net).render_frame(pose, aud, expr, lat, bc)
             assert np.array_equal(vid[i].numpy().reshape(-1, 3), (255 * np.clip(rgb.cpu().numpy(), 0, 1)).astype(np.uint8))
+
+
+def test_full_frame_bf16_psnr_gate(M):
+    """BASELINE.json config 2 at FULL size (450 x 450 = 202 500 rays, 64 + 128 samples, normalised-density preset): the bf16 tensor-core
+    render against the fp32 render of the same network -- north_star gate: PSNR delta <= 0.05 dB against a target image; plus max-abs
+    and the PSNR between the two renders themselves.  (The fp32 kernels are pinned to the reference by the golden tests above.)"""
+    from ideal_nerf_b200.frame import FrameRenderer
+    from ideal_nerf_b200 import synthetic as S
+    cam, fr = S.camera(), S.frame_inputs(0)
+    out = {}
+    for mode in ("fp32", "bf16"):
+        args = M.default_args(dim_aud=64, dim_expr=76, perturb=0., mlp_mode=mode, N_samples=64, N_importance=128, near=S.NEAR, far=S.FAR)
+        net = M.Network(450, 450, cam["focal"], S.NEAR, S.FAR, 1 << 20, None, 64, 128, args=args)
+        torch.manual_seed(1234)
+        net.apply(M.init_weights)
+        net = net.to(DEV).eval()
+        rays = M.ops.get_rays_packed(450, 450, cam["focal"], cam["c2w"].to(DEV), S.NEAR, S.FAR)[::197].contiguous()
+        if mode == "fp32":
+            for fn in (net.face_nerf_coarse, net.face_nerf_fine):
+                S.normalise_density_(fn, rays, fr["aud"].to(DEV), fr["expr"].to(DEV), fr["latent"].to(DEV))
+            sd = {k: v.clone() for k, v in net.state_dict().items()}
+        else:
+            net.load_state_dict(sd)
+        with torch.no_grad():
+            ret, _ = FrameRenderer(net).render_band(fr["pose"].to(DEV), fr["aud"].to(DEV), fr["expr"].to(DEV), fr["latent"].to(DEV),
+                                                    fr["bc_rgb"].to(DEV), perturb=0.)
+        out[mode] = {k: ret[k].float() for k in ("rgb_map", "last_weight", "rgb0")}
+    a, b = out["fp32"]["rgb_map"], out["bf16"]["rgb_map"]
+    assert a.shape == (202500, 3)
+    lw = out["fp32"]["last_weight"]              # weight of the background sample: acc_map itself is 1 (last alpha = 1)
+    assert 0.05 < float(lw.mean()) < 0.95, "preset must give a non-trivial image (neither all background nor opaque)"
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    tgt = (a + 0.05 * torch.randn(a.shape, device=DEV, generator=gen)).clamp(0, 1)        # a 'ground truth' 26 dB away from the render
+    d_psnr = abs(_psnr(b, tgt) - _psnr(a, tgt))
+    between = _psnr(b, a)
+    print(f"full frame: max-abs bf16-fp32 {float((a - b).abs().max()):.3e}, PSNR(bf16, fp32) {between:.1f} dB, PSNR delta vs target {d_psnr:.4f} dB")
+    assert d_psnr <= 0.05
+    assert between >= 40.0
+    assert abs(_psnr(out["bf16"]["rgb0"], tgt) - _psnr(out["fp32"]["rgb0"], tgt)) <= 0.05
