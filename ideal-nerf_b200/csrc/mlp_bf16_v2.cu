@@ -358,44 +358,26 @@ __global__ void __launch_bounds__(NT, 1) mlp_bf16_v2_kernel(MlpArgs a, int n_ray
                 tc_fence_after();
                 if (prof) { const long long q1 = clock64(); te_wait += q1 - q0; q0 = q1; }
                 const int nchunk = N >> 5;                        // 8 or 4
-                // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is converted and stored
-#ifndef V2_EXP
-#define V2_EXP 0
-#endif
-                uint32_t rbuf[2][32];
-                if (V2_EXP & 1) {
+                // NOT unrolled over the chunks: one ~1 KB body per layer kind that stays in the instruction cache (the unrolled form was
+                // 9 KB per pass, evicted between passes by the issuer's straight-line schedule: the F2FP block stalled on fetch)
+#pragma unroll 1
+                for (int c = 0; c < nchunk; ++c) {
+                    uint32_t r[32], pk[16];
+                    tmem_ld32(t_lane + c * 32, r);
+                    tmem_wait_ld();
+                    const int f0 = c * 32;
+                    switch (l) {
+                        case 7: epi_chunk<1>(r, pk, nullptr, s_aw + f0, nullptr, alpha, rgb0, rgb1, rgb2); break;
+                        case 8: epi_chunk<2>(r, pk, s_dirb + (slot * RMAX + ray_local) * 128 + f0, nullptr, nullptr, alpha, rgb0, rgb1, rgb2); break;
+                        case 10: epi_chunk<3>(r, pk, nullptr, nullptr, s_rw + f0, alpha, rgb0, rgb1, rgb2); break;
+                        default: epi_chunk<0>(r, pk, nullptr, nullptr, nullptr, alpha, rgb0, rgb1, rgb2); break;
+                    }
+                    if (l != 10) {                            // every MMA of this slot's layer has completed: rewrite in place
+                        uint8_t* kb = act + (f0 >> 6) * 16384 + row_off;
+                        const int ch0 = (f0 & 63) >> 3;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) rbuf[0][j] = rbuf[1][j] = (uint32_t)(lane * 77 + j + l);
-                } else tmem_ld32(t_lane, rbuf[0]);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    if (c < nchunk) {
-                        uint32_t pk[16];
-                        if (!(V2_EXP & 1)) {
-                            tmem_wait_ld();
-                            if (c + 1 < nchunk) tmem_ld32(t_lane + (c + 1) * 32, rbuf[(c + 1) & 1]);
-                        }
-                        const uint32_t (&r)[32] = rbuf[c & 1];
-                        const int f0 = c * 32;
-                        if (V2_EXP & 2) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) pk[j] = r[j] ^ r[j + 16];
-                        } else
-                        switch (l) {
-                            case 7: epi_chunk<1>(r, pk, nullptr, s_aw + f0, nullptr, alpha, rgb0, rgb1, rgb2); break;
-                            case 8: epi_chunk<2>(r, pk, s_dirb + (slot * RMAX + ray_local) * 128 + f0, nullptr, nullptr, alpha, rgb0, rgb1, rgb2); break;
-                            case 10: epi_chunk<3>(r, pk, nullptr, nullptr, s_rw + f0, alpha, rgb0, rgb1, rgb2); break;
-                            default: epi_chunk<0>(r, pk, nullptr, nullptr, nullptr, alpha, rgb0, rgb1, rgb2); break;
-                        }
-                        if (l != 10 && !(V2_EXP & 4)) {           // every MMA of this slot's layer has completed: rewrite in place
-                            uint8_t* kb = act + (f0 >> 6) * 16384 + row_off;
-                            const int ch0 = (f0 & 63) >> 3;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                *reinterpret_cast<uint4*>(kb + (((ch0 + q) ^ rsw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-                        } else if (V2_EXP & 4) {
-                            if (pk[3] == 0x12345678u) alpha += 1.f;      // keep the values alive
-                        }
+                        for (int q = 0; q < 4; ++q)
+                            *reinterpret_cast<uint4*>(kb + (((ch0 + q) ^ rsw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                     }
                 }
                 tc_fence_before();

@@ -273,6 +273,24 @@ __global__ void __launch_bounds__(384, 1) rate_kernel(Args p) {
         uint8_t* scr = sm + OFF_SCR + (row >> 3) * 1024 + (row & 7) * 128;
         long long loops = 0;
         uint32_t sink = 0;
+        if (p.interfere >= 3) {
+            // register-only work next to the MMAs: 64 cvt.rn.relu.bf16x2.f32 (interfere = 3) or 64 LOP3 (interfere = 4) per loop
+            float v[32];
+            for (int j = 0; j < 32; ++j) v[j] = (float)(threadIdx.x * 3 + j) * 0.37f - 5.f;
+            while (!stop_flag) {
+#pragma unroll
+                for (int rep = 0; rep < 4; ++rep)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        uint32_t q;
+                        if (p.interfere == 3) q = pack_bf16x2_relu(v[2 * j], v[2 * j + 1]);
+                        else q = __float_as_uint(v[2 * j]) ^ __float_as_uint(v[2 * j + 1]);
+                        sink ^= q;
+                        v[2 * j] += 1.0f;
+                    }
+                ++loops;
+            }
+        } else
         while (!stop_flag) {
             uint32_t packed[64];
 #pragma unroll
@@ -539,6 +557,9 @@ int main(int argc, char** argv) {
         rate_case<1, true>(256, 1, inter, G);
         rate_case<2, true>(256, 1, inter, G);
     }
+    rate_case<1, false>(128, 2, 3, G); rate_case<1, false>(128, 2, 4, G);
+    rate_case<1, false>(256, 2, 3, G); rate_case<1, false>(256, 2, 4, G);
+    rate_case<2, false>(256, 2, 3, G); rate_case<2, false>(256, 2, 4, G);
     rate_case<1, false>(128, 2, 0, G, 1);
     rate_case<1, false>(128, 2, 0, G, 2);
     rate_case<1, false>(128, 2, 1, G, 2);
