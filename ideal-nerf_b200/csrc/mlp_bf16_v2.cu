@@ -177,23 +177,27 @@ struct IssueCtx {
 };
 
 template <int L>
-__device__ __forceinline__ void issue_layer(IssueCtx& c, int slot) {
+__device__ __forceinline__ void issue_both(IssueCtx& c) {
     constexpr int N = lay_N(L), NKB = lay_act_kb(L), CNT = lay_cnt(L);
     constexpr uint32_t IDESC = umma_idesc_bf16(256, N);
     Bars* bars = c.bars;
-    // the slot's previous epilogue (both CTAs): accumulator drained, activations rewritten
     long long q0 = c.prof ? clock64() : 0;
-    if (c.n_layers[slot] > 0) wait_c(&bars->ebar[slot], (c.n_layers[slot] - 1) & 1);
-    if (L == 0 && slot == 0) wait_c(&bars->pe_ready, c.iter_ctr & 1);
+    // both slots' previous epilogues (both CTAs): accumulators drained, activations rewritten
+    if (c.n_layers[0] > 0) {
+        wait_c(&bars->ebar[0], (c.n_layers[0] - 1) & 1);
+        wait_c(&bars->ebar[1], (c.n_layers[1] - 1) & 1);
+    }
+    if (L == 0) wait_c(&bars->pe_ready, c.iter_ctr & 1);
     if (c.prof) { const long long q1 = clock64(); c.t_e += q1 - q0; q0 = q1; }
-    const uint32_t d = c.tmem_base + slot * 256;
-    // bias: D = ones[256 x 16] . tile[N x 16]^T, overwrites the accumulator
+    // bias: D = ones[256 x 16] . tile[N x 16]^T, overwrites both accumulators
     wait_l(&bars->bfull[c.bslot], c.bpar);
     wait_c(&bars->pbfull[c.bslot], c.bpar);
     tc_fence_after();
     if (c.prof) c.t_w += clock64() - q0;
     if (elect_one()) {
-        umma2(d, c.ones_lo, HI_NOSWZ, c.bt_lo + c.bslot * (4096 >> 4), HI_NOSWZ, IDESC, 0u);
+#pragma unroll
+        for (int slot = 0; slot < 2; ++slot)
+            umma2(c.tmem_base + slot * 256, c.ones_lo, HI_NOSWZ, c.bt_lo + c.bslot * (4096 >> 4), HI_NOSWZ, IDESC, 0u);
         commit2(&bars->bempty[c.bslot]);
     }
     __syncwarp();
@@ -209,23 +213,22 @@ __device__ __forceinline__ void issue_layer(IssueCtx& c, int slot) {
         if (c.prof) c.t_w += clock64() - q0;
         if (elect_one()) {
             const uint32_t b_lo = c.w_lo + c.stage * (STAGE_BYTES >> 4);
-            const uint32_t a_lo = is_pe ? c.pe_lo + slot * (16384 >> 4) : c.a_lo + slot * (65536 >> 4) + i * (16384 >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma2(d, a_lo + 2 * k, HI_SW128, b_lo + 2 * k, HI_SW128, IDESC, 1u);
-            commit2(&bars->wempty[c.stage]);
-            if (i == CNT - 1) {
-                commit2(&bars->cbar[slot]);
-                if (L == 5 && slot == 1) commit2(&bars->pe_free);
+            for (int slot = 0; slot < 2; ++slot) {
+                const uint32_t a_lo = is_pe ? c.pe_lo + slot * (16384 >> 4) : c.a_lo + slot * (65536 >> 4) + i * (16384 >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma2(c.tmem_base + slot * 256, a_lo + 2 * k, HI_SW128, b_lo + 2 * k, HI_SW128, IDESC, 1u);
+                if (i == CNT - 1) commit2(&bars->cbar[slot]);      // this slot's layer is complete: its epilogue may start
             }
+            commit2(&bars->wempty[c.stage]);
+            if (i == CNT - 1 && L == 5) commit2(&bars->pe_free);
         }
         __syncwarp();
         if (++c.stage == NS) { c.stage = 0; c.wpar ^= 1; }
     }
-    ++c.n_layers[slot];
+    ++c.n_layers[0];
+    ++c.n_layers[1];
 }
-
-template <int L>
-__device__ __forceinline__ void issue_both(IssueCtx& c) { issue_layer<L>(c, 0); issue_layer<L>(c, 1); }
 
 __global__ void __launch_bounds__(NT, 1) mlp_bf16_v2_kernel(MlpArgs a, int n_rays, int n_pairs) {
     extern __shared__ __align__(1024) uint8_t sm[];
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_bf16_v2_kernel(MlpArgs a, int n_ray
                 for (int l = 0; l < 11; ++l) {
                     const uint32_t nh = lay_N(l) >> 1;                     // my rows of the B operand
                     const uint32_t toff = l < 8 ? (2 * l + rank) * 4096u : 65536u + (2 * (l - 8) + rank) * 2048u;
-                    for (int slot = 0; slot < 2; ++slot) {
+                    {
                         const uint32_t bs = bh & 1;
                         wait_l(&bars->bempty[bs], ((bh >> 1) & 1) ^ 1);
                         mbar_arrive_expect_tx(&bars->bfull[bs], nh * 32u);
@@ -318,8 +321,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_bf16_v2_kernel(MlpArgs a, int n_ray
             // ================= relay (peer): tell the leader when MY half of a bias tile / weight stage has landed =================
             uint32_t g = 0, bh = 0;
             for (long long c0 = 2 * pair; c0 < n_chunks; c0 += 2 * n_pairs)
-                for (int l = 0; l < 11; ++l)
-                    for (int slot = 0; slot < 2; ++slot) {
+                for (int l = 0; l < 11; ++l) {
                         wait_l(&bars->bfull[bh & 1], (bh >> 1) & 1);
                         mbar_arrive_remote(&bars->pbfull[bh & 1], 0);
                         ++bh;
@@ -366,6 +368,11 @@ __global__ void __launch_bounds__(NT, 1) mlp_bf16_v2_kernel(MlpArgs a, int n_ray
                     tmem_ld32(t_lane + c * 32, r);
                     tmem_wait_ld();
                     const int f0 = c * 32;
+#ifndef V2_EXP
+#define V2_EXP 0
+#endif
+                    if (V2_EXP & 8) epi_chunk<0>(r, pk, nullptr, nullptr, nullptr, alpha, rgb0, rgb1, rgb2);
+                    else
                     switch (l) {
                         case 7: epi_chunk<1>(r, pk, nullptr, s_aw + f0, nullptr, alpha, rgb0, rgb1, rgb2); break;
                         case 8: epi_chunk<2>(r, pk, s_dirb + (slot * RMAX + ray_local) * 128 + f0, nullptr, nullptr, alpha, rgb0, rgb1, rgb2); break;
@@ -413,6 +420,12 @@ __global__ void __launch_bounds__(NT, 1) mlp_bf16_v2_kernel(MlpArgs a, int n_ray
         for (long long c0 = 2 * pair; c0 < n_chunks; c0 += 2 * n_pairs, ++iter_ctr) {
             const long long it = c0 + rank;
             uint32_t pk[2][32];
+            if (V2_EXP & 16) {
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) pk[sl][j] = 0x3c003c00u;
+            } else
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl) {
                 long long p = it * 256 + sl * 128 + t;

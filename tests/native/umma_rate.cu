@@ -238,11 +238,13 @@ __global__ void __launch_bounds__(384, 1) rate_kernel(Args p) {
         const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 3) * 256;
         uint8_t* scr = sm + OFF_SCR + (row >> 3) * 1024 + (row & 7) * 128;
         uint32_t sink = 0;
+        long long t_work = 0;
         for (int lc = 0; lc < p.iters; ++lc)
             for (int h = 0; h < 2; ++h) {
                 bounded_wait(&cbar[h], lc & 1);
                 __syncwarp();
                 tc_fence_after();
+                const long long w0 = clock64();
                 if (p.interfere) {
                     uint32_t packed[64];
 #pragma unroll
@@ -261,10 +263,11 @@ __global__ void __launch_bounds__(384, 1) rate_kernel(Args p) {
                     fence_proxy_async_smem();
                     sink += packed[3];
                 }
+                t_work += clock64() - w0;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ebar[h]);
             }
-        if (sink == 0x12345u) p.report[blockIdx.x * 4 + 3] = 1.f;
+        if (lane == 0 && warp == 4) p.report[blockIdx.x * 4 + 3] = (float)t_work / (2.f * p.iters) + (sink == 0x12345u ? 1.f : 0.f);
     } else if (warp >= 4 && warp < 12 && p.interfere) {
         // epilogue-like traffic: tcgen05.ld of 128 fp32 columns per row + 16 x 16-byte swizzled st.shared (interfere = 1)
         // or + tcgen05.st of 64 packed columns (interfere = 2)
@@ -520,9 +523,10 @@ void rate_case(int N, int slots, int interfere, int grid, int mimic = 0) {
     if (launch<CG, TS>(a, grid)) { cudaFree(rep); return; }
     std::vector<float> h(4096);
     cudaMemcpy(h.data(), rep, 4096 * 4, cudaMemcpyDeviceToHost);
-    double cyc = 0, nm = 0, loops = 0; int cnt = 0;
-    for (int b = 0; b < grid; b += CG) { cyc += h[b * 4]; nm += h[b * 4 + 1]; loops += h[b * 4 + 2]; ++cnt; }
-    cyc /= cnt; nm /= cnt; loops /= cnt;
+    double cyc = 0, nm = 0, loops = 0, epi = 0; int cnt = 0;
+    for (int b = 0; b < grid; b += CG) { cyc += h[b * 4]; nm += h[b * 4 + 1]; loops += h[b * 4 + 2]; epi += h[b * 4 + 3]; ++cnt; }
+    cyc /= cnt; nm /= cnt; loops /= cnt; epi /= cnt;
+    if (mimic >= 2) printf("[responder: %.0f cycles of work per half-layer epilogue (128 columns per row)] ", epi);
     const double mac = 128.0 * CG * N * 16, per = cyc / nm;
     if (mimic) printf("mimic=%d ", mimic);
     printf("rate %s cg%d N=%3d slots=%d interfere=%d grid=%3d: %7.1f cyc/MMA  -> %6.0f MAC/clk/SM (%.0f%% of 4096)   epilogue: %.0f rows-of-128col per kcyc per CTA\n",
