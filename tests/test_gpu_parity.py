@@ -852,3 +852,28 @@ def test_full_frame_bf16_psnr_gate(M):
     assert d_psnr <= 0.05
     assert between >= 40.0
     assert abs(_psnr(out["bf16"]["rgb0"], tgt) - _psnr(out["fp32"]["rgb0"], tgt)) <= 0.05
+
+
+def test_torso_nerf_bf16_forward_and_training(M):
+    """The torso network's geometry (dim_aud = 64 + 42 = 106, no expression / latent inputs, train_torso.py:213-221) through the bf16
+    tensor-core kernels: forward against the fp32 kernel, and one forward + backward (conditioning gradient has only the aud part)."""
+    b = O.synthetic_train_batch(0)
+    n, s = 70, 64
+    rays = b["rays"][:n].to(DEV)
+    sd = O.init_face_nerf(13, 106, 0, 0)
+    n16, n32 = head_net(M, sd, "bf16", dim_aud=106, dim_expr=0, dim_latent=0), head_net(M, sd, "fp32", dim_aud=106, dim_expr=0, dim_latent=0)
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    sig = torch.randn(106, device=DEV, generator=gen)
+    z = M.ops.sample_coarse(rays, s, torch.rand(n, s, device=DEV, generator=gen))
+    G = torch.randn(n, s, 4, device=DEV, generator=gen)
+    out = {}
+    for tag, net in (("bf16", n16), ("fp32", n32)):
+        a = sig.clone().requires_grad_(True)
+        raw = net.query(rays, z, a, None, None)
+        (raw * G).sum().backward()
+        out[tag] = (raw.detach(), a.grad, torch.cat([p.grad.reshape(-1) for p in net.parameters() if p.grad is not None]))
+    close(out["bf16"][0], out["fp32"][0], 3e-2 * max(1.0, float(out["fp32"][0].abs().max())), "torso raw bf16 vs fp32")
+    cos_w = float(torch.nn.functional.cosine_similarity(out["bf16"][2].double(), out["fp32"][2].double(), dim=0))
+    cos_a = float(torch.nn.functional.cosine_similarity(out["bf16"][1].double(), out["fp32"][1].double(), dim=0))
+    print(f"torso bf16 training: cos(weights grad) {cos_w:.5f}  cos(d_aud) {cos_a:.5f}")
+    assert cos_w >= 0.97 and cos_a >= 0.97
