@@ -785,15 +785,10 @@ int mlp_bf16_launch(const MlpArgs& a, bool embedded, cudaStream_t st) {
     if (a.s < 43) return fail(INERF_E_UNSUPPORTED, "bf16 mode needs at least 43 samples per ray (a 128-row slot may touch at most 4 rays)");
     if ((uintptr_t)a.packed & 15) return fail(INERF_E_ALIGN, "inerf_mlp_fwd: packed weights must be 16-byte aligned");
     static thread_local int configured_dev = -1;
-    static Schedule S;
-    static bool have_schedule = false;
+    // the step table does not depend on the conditioning dims; a function-local static is initialised once, thread-safely
+    static const Schedule S = [] { InerfNetDims d{64, 76, 32, 256, 8, 63, 27}; return build_schedule(&d); }();
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!have_schedule) {
-        InerfNetDims d{64, 76, 32, 256, 8, 63, 27};          // the step table does not depend on the conditioning dims
-        S = build_schedule(&d);
-        have_schedule = true;
-    }
     if (configured_dev != dev) {
         cudaError_t e = cudaFuncSetAttribute(mlp_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);

@@ -469,11 +469,10 @@ int mlp_bf16_bwd_pack(const InerfNetDims* d, const float* const* params_host, vo
 int mlp_bf16_bwd_chain_launch(const InerfNetDims* dims, const float* const* params_host, const void* packed_t, const uint32_t* mask,
                               const float* d_raw, uint8_t* delta_img, long long P, cudaStream_t st) {
     static thread_local int configured_dev = -1;
-    static BSchedule S;
-    static bool have = false;
+    // step sizes / offsets do not depend on the conditioning dims; a function-local static is initialised once, thread-safely
+    static const BSchedule S = [] { InerfNetDims d{64, 76, 32, 256, 8, 63, 27}; return build_bschedule(&d); }();
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!have) { S = build_bschedule(dims); have = true; }      // step sizes / offsets do not depend on the conditioning dims
     if (configured_dev != dev) {
         cudaError_t e = cudaFuncSetAttribute(mlp_bf16_bwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD);
         if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_bsteps, S.steps, sizeof(BStep) * MAX_BSTEPS);
