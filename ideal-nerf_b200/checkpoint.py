@@ -1,0 +1,46 @@
+"""Checkpoint formats of the reference's HeadNeRF training script, read and written with the same dictionary keys so files move both ways.
+
+* head.tar (NeRFs/HeadNeRF/train/audio_exp_nerf.py:584-591 save, :518-525 resume):
+      {'global_step', 'model_state_dict' (Network.state_dict(): face_nerf_coarse.*, face_nerf_fine.*, aud_net.*, aud_att_net.*,
+       ds_aud_net.*), 'optimizer', 'latent_codes' (n_frames, 32)}
+* fine-tune source (--ft_path, :498-514): {'network_fn_state_dict', 'network_fine_state_dict', 'network_audnet_state_dict',
+      'network_audattnet_state_dict'}; the reference drops pts_linears.0 / pts_linears.5 / views_linears.0 weights (their input
+      widths depend on dim_aud / dim_expr) and loads the rest with strict=False.
+Pure host I/O: nothing here launches a kernel."""
+import torch
+
+_FT_DROPPED = ("pts_linears.0.weight", "pts_linears.5.weight", "views_linears.0.weight")
+
+
+def save_head_checkpoint(path, network, optimizer, latent_codes, global_step):
+    """audio_exp_nerf.py:584-591."""
+    torch.save({"global_step": int(global_step), "model_state_dict": network.state_dict(),
+                "optimizer": optimizer.state_dict() if optimizer is not None else None,
+                "latent_codes": latent_codes.data if hasattr(latent_codes, "data") else latent_codes}, path)
+
+
+def load_head_checkpoint(path, network, optimizer=None, latent_codes=None, map_location=None, strict=True):
+    """audio_exp_nerf.py:518-525.  Returns global_step.  Weights written by the reference load unchanged (same keys)."""
+    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    network.load_state_dict(ckpt["model_state_dict"], strict=strict)
+    if latent_codes is not None and ckpt.get("latent_codes") is not None:
+        latent_codes.data = ckpt["latent_codes"].to(latent_codes.device)
+    if optimizer is not None and ckpt.get("optimizer") is not None:
+        optimizer.load_state_dict(ckpt["optimizer"])
+    return int(ckpt.get("global_step", 0))
+
+
+def load_finetune_checkpoint(path, network, map_location=None):
+    """audio_exp_nerf.py:498-514 (--ft_path)."""
+    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    coarse, fine = dict(ckpt["network_fn_state_dict"]), dict(ckpt["network_fine_state_dict"])
+    for k in _FT_DROPPED:
+        coarse.pop(k, None)
+        fine.pop(k, None)
+    network.face_nerf_coarse.load_state_dict(coarse, strict=False)
+    network.face_nerf_fine.load_state_dict(fine, strict=False)
+    if "network_audnet_state_dict" in ckpt:
+        network.aud_net.load_state_dict(ckpt["network_audnet_state_dict"], strict=False)
+    if "network_audattnet_state_dict" in ckpt:
+        network.aud_att_net.load_state_dict(ckpt["network_audattnet_state_dict"], strict=False)
+    return 0

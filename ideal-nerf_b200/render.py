@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
+from .audio_net import AudioNet, AudioAttNet
 from .face_nerf import FaceNeRF
 from .helper import config_parser, get_embedder
 
@@ -138,6 +139,15 @@ def render_rays(ray_batch, bc_rgb, aud_para, network_fn, network_query_fn=None, 
     return {k: v for k, v in ret.items() if k not in _PRIVATE}
 
 
+class _DeepSpeechAudNetKeys(nn.Module):
+    """models/audio_net.py:72-87, parameters only (state_dict compatibility): the reference uses it when dim_aud <= 29, which none of
+    its configurations does."""
+
+    def __init__(self):
+        super().__init__()
+        self.encoder_fc = nn.Sequential(nn.Linear(16, 1), nn.LeakyReLU(0.02, True))
+
+
 class Network(nn.Module):
     """Class-form HeadNeRF renderer, audio_exp_nerf.py:198.  ``args`` carries the reference's flags
     (helper.config_parser); the reference reads them from a module-level global."""
@@ -165,6 +175,30 @@ class Network(nn.Module):
                                        dim_latent=32, dim_expr=a.dim_expr, output_ch=self.output_ch,
                                        skips=self.skips, input_ch_views=input_ch_views,
                                        use_viewdirs=a.use_viewdirs, mlp_mode=mode)
+        # the conditioning nets of audio_exp_nerf.py:224-226, same attribute names so that head.tar's model_state_dict loads
+        self.aud_net = AudioNet(a.dim_aud, getattr(a, "win_size", 16))
+        self.aud_att_net = AudioAttNet()
+        self.ds_aud_net = _DeepSpeechAudNetKeys()
+
+    def audio_feature(self, auds, index, dataset_size, global_step=None):
+        """The per-frame audio code of audio_exp_nerf.py:241-266: the smo_size-frame window around `index` (zero padded at the ends of
+        the sequence) through AudioNet, then AudioAttNet; a single AudioNet call before `nosmo_iters`.  auds: (T, 16, 29) DeepSpeech
+        windows on the device.  Runs in the CUDA kernels of csrc/audio_net.cu (forward only)."""
+        a = self.args
+        if a.dim_aud <= 29:
+            raise NotImplementedError("dim_aud <= 29 (DeepSpeechAudNet) is not a configuration the reference's configs use")
+        with torch.no_grad():
+            if global_step is None or global_step >= getattr(a, "nosmo_iters", 0):
+                half = int(getattr(a, "smo_size", 8) / 2)
+                left, right = index - half, index + half
+                pad_l, pad_r = max(0, -left), max(0, right - dataset_size)
+                win = auds[max(left, 0):min(right, dataset_size)]
+                if pad_l:
+                    win = torch.cat((torch.zeros_like(win)[:pad_l], win), 0)
+                if pad_r:
+                    win = torch.cat((win, torch.zeros_like(win)[:pad_r]), 0)
+                return self.aud_att_net(self.aud_net(win.contiguous()))
+            return self.aud_net(auds[index:index + 1].contiguous())
 
     def set_mlp_mode(self, mode):
         for m in self.modules():
@@ -289,5 +323,8 @@ def pose_to_euler_trans(poses):
 def init_weights(m):
     """audio_exp_nerf.py:442-448."""
     if isinstance(m, nn.Linear):
+        torch.nn.init.xavier_uniform_(m.weight)
+        m.bias.data.fill_(0.01)
+    if isinstance(m, nn.Conv1d):
         torch.nn.init.xavier_uniform_(m.weight)
         m.bias.data.fill_(0.01)

@@ -226,6 +226,16 @@ int inerf_mlp_bwd_bf16(const InerfNetDims* dims, const float* const* params_host
                        const float* aud, const float* expr, const float* latent, const void* acts, const void* mask, void* deltas,
                        const float* d_raw, int64_t n_points, float* d_cond, void* scratch, void* stream);
 
+/* ---- per-frame conditioning nets (forward) -----------------------------------------------------------------------------------
+ * AudioNet: DeepSpeech windows x (n, 16, 29) -> audio codes y (n, dim_aud).  Replaces models/audio_net.py:43-69 as called from
+ * audio_exp_nerf.py:263,266.  params_host: 12 DEVICE pointers (host array) in state_dict order: encoder_conv.{0,2,4,6}.{weight,bias},
+ * encoder_fc1.{0,2}.{weight,bias} (nn.Conv1d (out,in,3) / nn.Linear (out,in) layouts). */
+int inerf_audio_net_fwd(const float* const* params_host, const float* x, int n, int dim_aud, float* y, void* stream);
+/* AudioAttNet: attention over the smoothing window, x (seq_len = 8, dim_feat) -> y (dim_feat); the attention convolutions see the
+ * first dim_att (32) channels.  Replaces models/audio_net.py:8-36 (audio_exp_nerf.py:264).  params_host: 12 device pointers:
+ * attentionConvNet.{0,2,4,6,8}.{weight,bias}, attentionNet.0.{weight,bias}. */
+int inerf_audio_att_fwd(const float* const* params_host, const float* x, int seq_len, int dim_feat, int dim_att, float* y, void* stream);
+
 /* After a failed inerf_mlp_fwd_trace (the trace build bounds every mbarrier wait to ~1 s and traps): the record
  * of the first waiter that timed out, {site code, block, thread, aux0, aux1, parity, 0, 0}; all zero otherwise.
  * HOST pointer to 8 ints. */

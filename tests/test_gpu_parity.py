@@ -877,3 +877,51 @@ def test_torso_nerf_bf16_forward_and_training(M):
     cos_a = float(torch.nn.functional.cosine_similarity(out["bf16"][1].double(), out["fp32"][1].double(), dim=0))
     print(f"torso bf16 training: cos(weights grad) {cos_w:.5f}  cos(d_aud) {cos_a:.5f}")
     assert cos_w >= 0.97 and cos_a >= 0.97
+
+
+def test_audio_conditioning_nets_golden(M, golden):
+    """AudioNet / AudioAttNet kernels against the outputs of the unmodified reference modules (tests/golden/make_golden_audio.py):
+    same state_dict keys (the reference's weights load with strict=True), the 8-frame smoothing window and the single-frame call."""
+    g = golden("audio_nets")
+    for d in (64, 76):
+        net = M.AudioNet(d, 16)
+        net.load_state_dict({k[len(f"an{d}."):]: torch.from_numpy(g[k]) for k in g
+                             if k.startswith(f"an{d}.") and k.split(".")[-1] in ("weight", "bias")}, strict=True)
+        net = net.to(DEV).eval()
+        with torch.no_grad():
+            close(net(C(g[f"an{d}.x"])), g[f"an{d}.y"], 2e-5, f"AudioNet({d}) window")
+            y1 = net(C(g[f"an{d}.x"])[:1])
+            assert y1.shape == (d,)
+            close(y1, g[f"an{d}.y1"], 2e-5, f"AudioNet({d}) single frame")
+    att = M.AudioAttNet()
+    att.load_state_dict({k[4:]: torch.from_numpy(g[k]) for k in g if k.startswith("att.") and k.split(".")[-1] in ("weight", "bias")},
+                        strict=True)
+    att = att.to(DEV).eval()
+    with torch.no_grad():
+        for d in (64, 76):
+            close(att(C(g[f"att.x{d}"])), g[f"att.y{d}"], 2e-5, f"AudioAttNet on {d}-wide codes")
+    with pytest.raises(NotImplementedError):
+        att(C(g["att.x64"]))                       # parameters require grad and autograd is recording: forward-only kernels refuse
+
+
+def test_network_audio_feature_window(M, golden):
+    """Network.audio_feature (audio_exp_nerf.py:241-266): the zero-padded 8-frame window -> AudioNet -> AudioAttNet, against the same
+    composition of the reference modules' golden outputs at an interior frame, and the padding at both ends of the sequence."""
+    g = golden("audio_nets")
+    net = M.Network(450, 450, 1200., O.NEAR, O.FAR, 8192, None, 64, 128, args=M.default_args(dim_aud=64, dim_expr=76, nosmo_iters=0))
+    net.aud_net.load_state_dict({k[5:]: torch.from_numpy(g[k]) for k in g if k.startswith("an64.") and k.split(".")[-1] in ("weight", "bias")})
+    net.aud_att_net.load_state_dict({k[4:]: torch.from_numpy(g[k]) for k in g if k.startswith("att.") and k.split(".")[-1] in ("weight", "bias")})
+    net = net.to(DEV).eval()
+    x = C(g["an64.x"])                                   # (8, 16, 29)
+    auds = torch.cat([torch.randn(3, 16, 29, device=DEV), x, torch.randn(2, 16, 29, device=DEV)], 0)      # 13 frames, window of frame 7 = x
+    with torch.no_grad():
+        f = net.audio_feature(auds, 7, 13, global_step=10)
+        ref = net.aud_att_net(C(g["an64.y"]))            # attention over the reference's own AudioNet outputs
+        close(f, ref, 2e-5, "interior window")
+        f0 = net.audio_feature(auds, 1, 13, global_step=10)                                            # frames [-3, 5): three zero windows first
+        win = torch.cat([torch.zeros(3, 16, 29, device=DEV), auds[0:5]], 0)
+        close(f0, net.aud_att_net(net.aud_net(win)), 1e-6, "left padding")
+        f1 = net.audio_feature(auds, 12, 13, global_step=10)                                           # frames [8, 16): three zero windows last
+        win = torch.cat([auds[8:13], torch.zeros(3, 16, 29, device=DEV)], 0)
+        close(f1, net.aud_att_net(net.aud_net(win)), 1e-6, "right padding")
+        assert f.shape == (64,)

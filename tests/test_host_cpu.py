@@ -112,3 +112,38 @@ def test_config_flags(M, tmp_path):
     a = p.parse_args(["--config", str(cfg), "--N_rand", "1024"])
     assert a.N_samples == 64 and a.lrate == 3e-4 and a.mouth_rays == 512 and a.dim_expr == 79
     assert a.N_rand == 1024 and abs(a.near - 0.5674083709716797) < 1e-15
+
+
+def test_network_state_dict_matches_reference_keys_and_checkpoint_round_trip(M, tmp_path):
+    """head.tar layout (audio_exp_nerf.py:584-591): the Network exposes the reference's parameter names -- FaceNeRF x2, AudioNet,
+    AudioAttNet, DeepSpeechAudNet -- and a checkpoint written with the reference's keys round-trips; --ft_path files load with the three
+    width-dependent weights dropped (:498-514)."""
+    import torch
+    from ideal_nerf_b200 import checkpoint as ck
+    net = M.Network(450, 450, 1200., 0.57, 1.17, 8192, None, 64, 128)
+    keys = set(net.state_dict())
+    for k in ("aud_net.encoder_conv.0.weight", "aud_net.encoder_conv.6.bias", "aud_net.encoder_fc1.2.weight",
+              "aud_att_net.attentionConvNet.8.weight", "aud_att_net.attentionNet.0.bias", "ds_aud_net.encoder_fc.0.weight"):
+        assert k in keys, k
+    assert net.aud_net.encoder_fc1[2].weight.shape == (64, 64) and net.aud_att_net.attentionConvNet[0].weight.shape == (16, 32, 3)
+    lat = torch.ones(5, 32)
+    opt = torch.optim.Adam(list(net.parameters()) + [lat], lr=3e-4)
+    p = str(tmp_path / "head.tar")
+    ck.save_head_checkpoint(p, net, opt, lat * 2, 1234)
+    raw = torch.load(p, weights_only=False)
+    assert set(raw) == {"global_step", "model_state_dict", "optimizer", "latent_codes"}
+    net2 = M.Network(450, 450, 1200., 0.57, 1.17, 8192, None, 64, 128)
+    lat2 = torch.zeros(5, 32)
+    assert ck.load_head_checkpoint(p, net2, None, lat2) == 1234
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), net2.state_dict().values()))
+    assert torch.equal(lat2, lat * 2)
+    # fine-tune source with a different conditioning width: first-layer weights are dropped, everything else loads
+    src = M.Network(450, 450, 1200., 0.57, 1.17, 8192, None, 64, 128, args=M.default_args(dim_aud=64, dim_expr=0))
+    ft = str(tmp_path / "ft.tar")
+    torch.save({"network_fn_state_dict": src.face_nerf_coarse.state_dict(), "network_fine_state_dict": src.face_nerf_fine.state_dict(),
+                "network_audnet_state_dict": src.aud_net.state_dict(), "network_audattnet_state_dict": src.aud_att_net.state_dict()}, ft)
+    before = net2.face_nerf_coarse.pts_linears[0].weight.clone()
+    ck.load_finetune_checkpoint(ft, net2)
+    assert torch.equal(net2.face_nerf_coarse.pts_linears[0].weight, before)                      # dropped key: untouched
+    assert torch.equal(net2.face_nerf_coarse.pts_linears[1].weight, src.face_nerf_coarse.pts_linears[1].weight)
+    assert torch.equal(net2.aud_net.encoder_conv[0].weight, src.aud_net.encoder_conv[0].weight)
