@@ -44,6 +44,7 @@ SIGNATURES = {
     "inerf_last_error": (ctypes.c_char_p, []),
     "inerf_device_check": (_I, []),
     "inerf_get_rays": (_I, [_I, _I, _F, _F, _F, _P, _I, _F, _F, _P, _P]),
+    "inerf_get_rays_at": (_I, [_P, _I, _F, _F, _F, _P, _I, _F, _F, _P, _P]),
     "inerf_pack_rays": (_I, [_P, _P, _I, _F, _F, _P, _P]),
     "inerf_posenc": (_I, [_P, _L, _I, _I, _P, _P]),
     "inerf_to8b": (_I, [_P, _L, _P, _P]),

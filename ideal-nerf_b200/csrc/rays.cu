@@ -49,6 +49,37 @@ __global__ void pack_rays_kernel(const float* __restrict__ o, const float* __res
               d[idx * 3 + 2], near_, far_);
 }
 
+// Rays of SELECTED pixels only (training batches): the reference builds the full H x W ray grid for every sample and then indexes
+// N_rand of them (audio_exp_nerf.py:123-139,189-191); same arithmetic as get_rays_kernel, one thread per selected pixel.
+__global__ void get_rays_at_kernel(const long long* __restrict__ coords, int n, float focal, float cx, float cy,
+                                   const float* __restrict__ c2w, int rs, float near_, float far_, float* __restrict__ rays) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const float row = (float)coords[2 * idx], col = (float)coords[2 * idx + 1];
+    float c0 = __fdiv_rn(__fsub_rn(col, cx), focal);
+    float c1 = -__fdiv_rn(__fsub_rn(row, cy), focal);
+    float c2 = -1.0f;
+    float d[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        float a = __fmul_rn(c0, c2w[r * rs + 0]);
+        float b = __fmul_rn(c1, c2w[r * rs + 1]);
+        float c = __fmul_rn(c2, c2w[r * rs + 2]);
+        d[r] = __fadd_rn(__fadd_rn(a, b), c);
+    }
+    store_ray(rays + (size_t)idx * 11, c2w[3], c2w[rs + 3], c2w[2 * rs + 3], d[0], d[1], d[2], near_, far_);
+}
+
+extern "C" int inerf_get_rays_at(const int64_t* coords, int n, float focal, float cx, float cy, const float* c2w, int c2w_row_stride,
+                                 float near_, float far_, float* rays, void* stream) {
+    if (n < 0 || c2w_row_stride < 4) return fail(INERF_E_SHAPE, "inerf_get_rays_at: bad n / c2w_row_stride");
+    if (n == 0) return INERF_OK;
+    if (!coords || !c2w || !rays) return fail(INERF_E_ARG, "inerf_get_rays_at: NULL pointer");
+    get_rays_at_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(coords), n, focal, cx, cy, c2w,
+                                                                      c2w_row_stride, near_, far_, rays);
+    return check_launch("inerf_get_rays_at");
+}
+
 extern "C" int inerf_get_rays(int H, int W, float focal, float cx, float cy, const float* c2w, int c2w_row_stride,
                               float near_, float far_, float* rays, void* stream) {
     if (!c2w || !rays) return fail(INERF_E_ARG, "inerf_get_rays: NULL pointer");

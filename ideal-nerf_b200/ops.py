@@ -94,6 +94,19 @@ def get_rays_packed(H, W, focal, c2w, near, far, cx=None, cy=None):
     return rays
 
 
+def get_rays_at(coords, focal, c2w, near, far, cx, cy):
+    """(n, 11) packed rays of the selected pixels; coords (n, 2) int64 = (row, col).  Same bits as get_rays_packed(...)[row * W + col]."""
+    _need_cuda(coords, "coords")
+    coords = coords.to(torch.int64).contiguous()
+    c2w = f32c(c2w, "c2w")
+    n = coords.shape[0]
+    rays = torch.empty((n, 11), device=c2w.device, dtype=torch.float32)
+    with torch.cuda.device(c2w.device):
+        call("inerf_get_rays_at", _lib.lib().inerf_get_rays_at, ptr(coords), n, float(focal), float(cx), float(cy), ptr(c2w), c2w.stride(0),
+             float(near), float(far), ptr(rays), stream())
+    return rays
+
+
 def pack_rays(rays_o, rays_d, near, far):
     rays_o = f32c(rays_o.reshape(-1, 3), "rays_o")
     rays_d = f32c(rays_d.reshape(-1, 3), "rays_d")

@@ -86,6 +86,11 @@ int inerf_device_check(void);
 int inerf_get_rays(int H, int W, float focal, float cx, float cy, const float* c2w, int c2w_row_stride,
                    float near_, float far_, float* rays, void* stream);
 
+/* The same rays for n SELECTED pixels only: coords (n,2) int64 = (row, col).  Replaces the full-grid get_rays + index of the
+ * training sampler (audio_exp_nerf.py:123-139 + :189-191).  rays: (n, 11). */
+int inerf_get_rays_at(const int64_t* coords, int n, float focal, float cx, float cy, const float* c2w, int c2w_row_stride,
+                      float near_, float far_, float* rays, void* stream);
+
 /* Ray packing from caller-supplied origins/directions (training batches).
  * Replaces audio_exp_nerf.py:409-427.  rays_o, rays_d: (n,3); rays: (n,11). */
 int inerf_pack_rays(const float* rays_o, const float* rays_d, int n, float near_, float far_, float* rays,

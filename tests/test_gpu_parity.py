@@ -925,3 +925,47 @@ def test_network_audio_feature_window(M, golden):
         win = torch.cat([auds[8:13], torch.zeros(3, 16, 29, device=DEV)], 0)
         close(f1, net.aud_att_net(net.aud_net(win)), 1e-6, "right padding")
         assert f.shape == (64,)
+
+
+def test_dataset_formats_and_selected_pixel_rays(M, tmp_path):
+    """a synthetic subject in the reference's on-disk layout (transforms_exp_train.json, aud.npy, bc.jpg, head_imgs/,
+    ori_imgs/*.lms, parsing/*.png) through HeadDataset == GetData (audio_exp_nerf.py:45-196): region budgets of sample_rays, rays of the
+    selected pixels bit-equal to the full-grid get_rays at those pixels, targets in cv2's BGR order, auds table, poses."""
+    import json
+    from PIL import Image
+    from ideal_nerf_b200.data import HeadDataset
+    H = W = 128
+    d = tmp_path / "subject"
+    for sub in ("head_imgs", "ori_imgs", "parsing"):
+        (d / sub).mkdir(parents=True)
+    rng = np.random.RandomState(0)
+    frames = []
+    for i in range(3):
+        Image.fromarray(rng.randint(0, 255, (H, W, 3), dtype=np.uint8)).save(d / "head_imgs" / f"{i}.jpg", quality=95)
+        parse = np.zeros((H, W, 3), np.uint8); parse[110:, :, 0] = 255                    # torso rows (pure red)
+        Image.fromarray(parse).save(d / "parsing" / f"{i}.png")
+        lms = rng.rand(68, 2) * 10 + 20; lms[48:] = rng.rand(20, 2) * 6 + np.array([60., 58.])     # mouth around rows 60..66, cols 58..64
+        np.savetxt(d / "ori_imgs" / f"{i}.lms", lms)
+        pose = np.eye(4); pose[:3, 3] = [0.01 * i, -0.02, 0.7772]
+        frames.append({"img_id": i, "aud_id": i + 5, "transform_matrix": pose.tolist(), "face_rect": [20, 24, 80, 76], "exp": rng.randn(76).tolist()})
+    json.dump({"focal_len": 340.0, "cx": W / 2, "cy": H / 2, "frames": frames}, open(d / "transforms_exp_train.json", "w"))
+    np.save(d / "aud.npy", rng.randn(6, 16, 29).astype(np.float32))
+    Image.fromarray(rng.randint(0, 255, (H, W, 3), dtype=np.uint8)).save(d / "bc.jpg", quality=95)
+    args = M.default_args(N_rand=600, mouth_rays=100, torso_rays=50, sample_rate=0.95, gt_dirs="head_imgs")
+    ds = HeadDataset(str(d), "aud.npy", "train", args)
+    assert len(ds) == 3 and ds.auds.shape == (3, 16, 29) and (ds.H, ds.W) == (H, W)
+    assert torch.equal(ds.auds[2].cpu(), torch.from_numpy(np.load(d / "aud.npy")[5]))           # aud_id clamps to the last window
+    np.random.seed(3)
+    batch_rays, target_s, bc_rgb, auds, raw_img, pose, exp, index = ds[1]
+    assert batch_rays.shape == (2, 600, 3) and target_s.shape == (600, 3) and bc_rgb.shape == (600, 3) and exp.shape == (76,)
+    np.random.seed(3)                                                                           # replay the draws
+    sel = ds.sample_pixels(ds.all_face_rects[1], np.loadtxt(ds.all_landmarks[1]), np.asarray(Image.open(ds.all_parse_imgs[1]).convert("RGB")))
+    n_rect = int((600 - 150) * 0.95)
+    in_rect = (sel[:, 0] >= 20) & (sel[:, 0] <= 100) & (sel[:, 1] >= 24) & (sel[:, 1] <= 100)
+    assert in_rect[:n_rect].all() and not in_rect[n_rect:450].any()                             # face rectangle, then outside it
+    assert (sel[600 - 50:, 0] >= 110).all()                                                      # torso rows last
+    full = M.ops.get_rays_packed(H, W, 340.0, torch.tensor(pose, dtype=torch.float32, device=DEV), 0.0, 1.0, W / 2, H / 2)
+    pick = full[torch.from_numpy(sel[:, 0] * W + sel[:, 1]).to(DEV)]
+    assert torch.equal(batch_rays[0], pick[:, 0:3]) and torch.equal(batch_rays[1], pick[:, 3:6])
+    img = np.asarray(Image.open(ds.all_imgs[1]).convert("RGB"))[:, :, ::-1]                     # BGR like cv2.imread
+    assert np.allclose(target_s.cpu().numpy(), img[sel[:, 0], sel[:, 1]] / 255.0, atol=1e-7)
