@@ -188,12 +188,13 @@ def train_step_bench(M, dev, steps, mode="bf16"):
     bc, tgt = fr["bc_rgb"].to(dev)[idx].contiguous(), torch.rand(3072, 3, generator=g).to(dev)
     aud, expr = fr["aud"].to(dev), fr["expr"].to(dev)
     lat = torch.ones(32, device=dev, requires_grad=True)
-    opt = torch.optim.Adam(list(net.parameters()) + [lat], lr=3e-4, betas=(0.9, 0.999))
+    from ideal_nerf_b200 import train as T
+    opt = torch.optim.Adam(list(net.parameters()) + [lat], lr=3e-4, betas=(0.9, 0.999), fused=True)
 
     def step():
         opt.zero_grad(set_to_none=True)
         r = net.render_rays(rays, bc, aud, None, lat, expr)
-        loss = torch.mean((r["rgb_map"] - tgt) ** 2) + torch.mean((r["rgb0"] - tgt) ** 2) + 10 * 0.0005 * torch.norm(lat)
+        loss = T.head_loss(r, tgt, lat, 0.0005)[0]            # mse(rgb) + mse(rgb0) + 10 * lc_weight * ||latent||  (:540-548)
         loss.backward()
         opt.step()
         return loss
@@ -211,7 +212,7 @@ def train_step_bench(M, dev, steps, mode="bf16"):
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     return {"rays_per_s": 3072 / (ms * 1e-3), "ms_per_step": ms, "n_rand": 3072, "mlp_mode": mode, "optimizer": "Adam lr=3e-4",
-            "loss": float(loss), "gpu_launches_per_step": ops.LAUNCHES["count"] / steps,
+            "loss": float(loss.detach()), "gpu_launches_per_step": ops.LAUNCHES["count"] / steps,
             "kernels_ms_per_step": {k: round(v[1] / steps, 3) for k, v in kt.summary().items()}}
 
 

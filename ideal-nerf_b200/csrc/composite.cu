@@ -417,3 +417,42 @@ extern "C" int inerf_composite_bwd(const float* raw, const float* z, const float
                        g_acc, g_depth, g_weights, g_rgb_fg, (float4*)d_raw)));
     return check_launch("inerf_composite_bwd");
 }
+
+// ---------------------------------------------------------------------------------------------
+// training loss seed: img_loss + img_loss0 of audio_exp_nerf.py:540-546 and its gradient in one pass
+// ---------------------------------------------------------------------------------------------
+// loss[0] = mean((rgb - t)^2), loss[1] = mean((rgb0 - t)^2)  (F.mse_loss over all 3n elements);  g = 2 (x - t) / (3n) for both maps.
+__global__ void __launch_bounds__(256) mse_pair_kernel(const float* __restrict__ rgb, const float* __restrict__ rgb0,
+                                                       const float* __restrict__ tgt, long long m, float inv_m, float* __restrict__ g_rgb,
+                                                       float* __restrict__ g_rgb0, float* __restrict__ loss) {
+    float s0 = 0.f, s1 = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+        const float t = tgt[i], d0 = rgb[i] - t, d1 = rgb0[i] - t;
+        s0 = fmaf(d0, d0, s0);
+        s1 = fmaf(d1, d1, s1);
+        g_rgb[i] = 2.0f * d0 * inv_m;
+        g_rgb0[i] = 2.0f * d1 * inv_m;
+    }
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    __shared__ float sh[2][8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { sh[0][w] = s0; sh[1][w] = s1; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        float t = 0.f;
+        for (int j = 0; j < 8; ++j) t += sh[threadIdx.x][j];
+        atomicAdd(loss + threadIdx.x, t * inv_m);
+    }
+}
+
+extern "C" int inerf_mse_pair(const float* rgb, const float* rgb0, const float* target, int64_t n_elems, float* g_rgb, float* g_rgb0,
+                              float* loss2, void* stream) {
+    if (n_elems <= 0) return fail(INERF_E_SHAPE, "inerf_mse_pair: need at least one element");
+    if (!rgb || !rgb0 || !target || !g_rgb || !g_rgb0 || !loss2) return fail(INERF_E_ARG, "inerf_mse_pair: NULL pointer");
+    cudaError_t e = cudaMemsetAsync(loss2, 0, 2 * sizeof(float), as_stream(stream));
+    if (e != cudaSuccess) { set_error("inerf_mse_pair: %s", cudaGetErrorString(e)); return (int)e; }
+    const int grid = (int)((n_elems + 255) / 256 < 4 * (long long)num_sms() ? (n_elems + 255) / 256 : 4 * (long long)num_sms());
+    mse_pair_kernel<<<grid, 256, 0, as_stream(stream)>>>(rgb, rgb0, target, n_elems, 1.0f / (float)n_elems, g_rgb, g_rgb0, loss2);
+    return check_launch("inerf_mse_pair");
+}

@@ -42,6 +42,8 @@ class FaceNeRF(nn.Module):
         self._dims = ops.net_dims(dim_aud, dim_expr, dim_latent)
         self._packed = None
         self._packed_key = None
+        self._packed_t = None
+        self._packed_t_key = None
 
     # -- plumbing -------------------------------------------------------------------------------
     def kernel_params(self):
@@ -59,6 +61,17 @@ class FaceNeRF(nn.Module):
             return MODES[self.mlp_mode]
         except KeyError:
             raise ValueError(f"mlp_mode must be one of {sorted(MODES)}, got {self.mlp_mode!r}")
+
+    def invalidate_packed(self):
+        """Drop the cached packed weights.  The cache key is (data_ptr, _version) of every parameter, which in-place updates that bypass
+        autograd's version counters do not change -- torch.optim.Adam(fused=True) is one -- so the training path never trusts it (it
+        re-packs on every call and invalidates afterwards) and train() / eval() switches drop it as well."""
+        self._packed = self._packed_key = None
+        self._packed_t = self._packed_t_key = None
+
+    def train(self, mode=True):
+        self.invalidate_packed()
+        return super().train(mode)
 
     def packed_weights(self, params):
         """Mode-specific packed weights, re-packed whenever a parameter was updated in place."""
@@ -126,10 +139,12 @@ class _MlpFn(torch.autograd.Function):
             if mode == _lib.INERF_MLP_BF16:
                 if embedded:
                     raise NotImplementedError("bf16 training runs through the fused (rays, z) entry; FaceNeRF.forward on embedded rows trains in mlp_mode='fp32'")
+                net.invalidate_packed()                       # optimiser steps may not bump parameter versions (fused Adam)
                 out, acts, mask, n_points = ops.mlp_fwd_train_bf16(net._dims, pd, net.packed_weights(params), cond, a, b)
                 ctx.n_points, ctx.bf16 = n_points, True
                 ctx.save_for_backward(acts, mask, *[t for t in (aud_d, expr_d, lat_d) if t is not None], *pd)
                 ctx.packed_t = net.packed_weights_bwd(params)
+                net.invalidate_packed()                       # ... and the next inference call must not reuse this step's pack
                 return out
             out, acts, n_points = ops.mlp_fwd_train(net._dims, pd, cond, x=a) if embedded else \
                 ops.mlp_fwd_train(net._dims, pd, cond, rays=a, z=b)

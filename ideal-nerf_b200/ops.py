@@ -212,6 +212,31 @@ def composite(raw, z, rays_d, bc_rgb, noise=None, white_bkgd=False, with_fg=Fals
     return _Composite.apply(raw, z, rays_d, bc_rgb, noise, white_bkgd, with_fg)
 
 
+class _MsePair(torch.autograd.Function):
+    """img_loss + img_loss0 (audio_exp_nerf.py:540-546): one kernel computes both means and both gradients."""
+
+    @staticmethod
+    def forward(ctx, rgb, rgb0, target):
+        a, b, t = f32c(rgb, "rgb"), f32c(rgb0, "rgb0"), f32c(target, "target")
+        assert a.shape == b.shape == t.shape
+        ga, gb = torch.empty_like(a), torch.empty_like(b)
+        loss2 = torch.empty((2,), device=a.device)
+        with torch.cuda.device(a.device):
+            call("inerf_mse_pair", _lib.lib().inerf_mse_pair, ptr(a), ptr(b), ptr(t), a.numel(), ptr(ga), ptr(gb), ptr(loss2), stream())
+        ctx.save_for_backward(ga, gb)
+        return loss2
+
+    @staticmethod
+    def backward(ctx, g):
+        ga, gb = ctx.saved_tensors
+        return ga * g[0], gb * g[1], None
+
+
+def mse_pair(rgb, rgb0, target):
+    """(F.mse_loss(rgb, target), F.mse_loss(rgb0, target)) as a 2-vector, differentiable in rgb and rgb0."""
+    return _MsePair.apply(rgb, rgb0, target)
+
+
 class _Blend(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rgb_head, lw, fg):

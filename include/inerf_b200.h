@@ -130,6 +130,12 @@ int inerf_composite_bwd(const float* raw, const float* z, const float* rays_d, i
                         const float* g_rgb, const float* g_disp, const float* g_acc, const float* g_depth,
                         const float* g_weights, const float* g_rgb_fg, float* d_raw, void* stream);
 
+/* Training loss seed: loss2[0] = F.mse_loss(rgb, target), loss2[1] = F.mse_loss(rgb0, target) and their gradients
+ * g = 2 (x - target) / n_elems in one pass.  Replaces audio_exp_nerf.py:540-546 (and the first backward nodes of :550).
+ * rgb, rgb0, target, g_rgb, g_rgb0: n_elems floats (n_elems = 3 * N_rand); loss2: 2 floats (zeroed here). */
+int inerf_mse_pair(const float* rgb, const float* rgb0, const float* target, int64_t n_elems, float* g_rgb, float* g_rgb0,
+                   float* loss2, void* stream);
+
 /* Head/torso blend rgb = rgb_head * last_weight_torso[:,None] + rgb_fg_torso.
  * Replaces train_torso.py:269-270 / test_torso.py:523. */
 int inerf_head_torso_blend(const float* rgb_head, const float* last_weight_torso, const float* rgb_fg_torso,

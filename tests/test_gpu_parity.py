@@ -969,3 +969,66 @@ def test_dataset_formats_and_selected_pixel_rays(M, tmp_path):
     assert torch.equal(batch_rays[0], pick[:, 0:3]) and torch.equal(batch_rays[1], pick[:, 3:6])
     img = np.asarray(Image.open(ds.all_imgs[1]).convert("RGB"))[:, :, ::-1]                     # BGR like cv2.imread
     assert np.allclose(target_s.cpu().numpy(), img[sel[:, 0], sel[:, 1]] / 255.0, atol=1e-7)
+
+
+def test_train_step_shell_matches_reference_formulas(M, golden):
+    """ops.mse_pair against F.mse_loss (values and gradients), head_loss against the golden training step of the unmodified
+    reference (loss value), the learning-rate schedule of audio_exp_nerf.py:554-558, and a few TrainStep iterations reducing the loss."""
+    from ideal_nerf_b200 import train as T
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    a, b, t = (torch.rand(777, 3, device=DEV, generator=gen) for _ in range(3))
+    a1, b1 = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    l2 = M.ops.mse_pair(a1, b1, t)
+    (l2[0] + 3.0 * l2[1]).backward()
+    a2, b2 = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    r0, r1 = torch.nn.functional.mse_loss(a2, t), torch.nn.functional.mse_loss(b2, t)
+    (r0 + 3.0 * r1).backward()
+    close(l2[0], r0, 1e-6, "mse rgb"); close(l2[1], r1, 1e-6, "mse rgb0")
+    close(a1.grad, a2.grad, 1e-8, "d mse / d rgb"); close(b1.grad, b2.grad, 1e-8, "d mse / d rgb0")
+    g, tr = golden("render_3072"), golden("train_step")
+    net = _preset_nets(M, g, "dense").train()
+    idx = C(tr["idx"])
+    lat = C(g["latent"]).clone().requires_grad_(True)
+    r = net.render_rays(C(g["rays"])[idx], C(g["bc_rgb"])[idx], C(g["aud"]), None, lat, C(g["expr"]), perturb=0.)
+    loss, _, _ = T.head_loss(r, C(g["target"])[idx], lat, 0.0005)
+    close(loss, tr["loss"], 2e-5, "loss of the golden training step")
+    args = M.default_args(dim_aud=64, dim_expr=76, perturb=0.0, lrate=3e-3, lrate_decay=500, mlp_mode="bf16")
+    assert abs(T.learning_rate(args, 0) - 3e-3) < 1e-12 and abs(T.learning_rate(args, 750000) - 3e-4) < 1e-12
+    b_ = O.synthetic_train_batch(0)
+    sel = torch.arange(0, 3072, 12)
+    net2 = M.Network(450, 450, 1200., O.NEAR, O.FAR, 8192, None, 64, 128, args=args)
+    torch.manual_seed(0)
+    net2.apply(M.init_weights)
+    net2 = net2.to(DEV).train()
+    step = T.TrainStep(net2, torch.ones(4, 32, device=DEV), args)
+    losses = [float(step(b_["rays"][sel].to(DEV), b_["bc_rgb"][sel].to(DEV), b_["target"][sel].to(DEV), b_["aud"].to(DEV),
+                         b_["expr"].to(DEV), 2)["loss"]) for _ in range(6)]
+    print("TrainStep losses", losses)
+    assert losses[-1] < losses[0] and all(np.isfinite(losses)) and step.global_step == 6
+
+
+def test_packed_weights_follow_fused_optimizer_updates(M):
+    """torch.optim.Adam(fused=True) updates parameters without bumping their autograd version, which is what the packed-weight cache is
+    keyed on: the bf16 training path must re-pack every step and the render after training must see the new weights."""
+    b = O.synthetic_train_batch(0)
+    rays = b["rays"][:64].to(DEV)
+    net = head_net(M, O.init_face_nerf(7), "bf16")
+    aud, expr, lat = b["aud"].to(DEV), b["expr"].to(DEV), b["latent"].to(DEV)
+    z = M.ops.sample_coarse(rays, 64)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-2, fused=True)
+    with torch.no_grad():
+        before = net.query(rays, z, aud, expr, lat)
+    outs = []
+    for _ in range(2):
+        opt.zero_grad()
+        raw = net.query(rays, z, aud, expr, lat)
+        outs.append(raw.detach().clone())
+        raw.square().mean().backward()
+        opt.step()
+    assert not torch.equal(outs[0], outs[1]), "the second training forward must use the updated weights"
+    with torch.no_grad():
+        after = net.eval().query(rays, z, aud, expr, lat)
+    fresh = head_net(M, {k: v.detach().cpu() for k, v in net.state_dict().items()}, "bf16")
+    with torch.no_grad():
+        assert torch.equal(after, fresh.query(rays, z, aud, expr, lat)), "inference after training must re-pack"
+    assert not torch.equal(before, after)
