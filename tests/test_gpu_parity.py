@@ -763,7 +763,7 @@ def test_bf16_training_loop_reduces_loss(M):
     assert abs(losses["bf16"][-1] - losses["fp32"][-1]) <= 0.05 * abs(losses["fp32"][0]), "bf16 and fp32 training must track each other"
 
 
-@pytest.mark.parametrize("n,s", [(8, 64), (301, 64), (47, 45), (333, 192)])
+@pytest.mark.parametrize("n,s", [(1, 64), (3, 43), (8, 64), (301, 64), (47, 45), (333, 192)])
 def test_bf16_pair_kernel_v2_bit_matches_v1(M, n, s):
     """The experimental cta_group::2 kernel (csrc/mlp_bf16_v2.cu, INERF_MLP_V2=1: CTA pairs, M = 256 MMAs over the whole layer width,
     slots alternating, remote mbarrier arrivals) reads the same packed blob and bias tiles and must return the same bits as v1,
@@ -785,6 +785,11 @@ def test_bf16_pair_kernel_v2_bit_matches_v1(M, n, s):
             os.environ["INERF_MLP_V2"] = old
     assert torch.isfinite(r2).all()
     assert torch.equal(r1, r2)
+    # and both against the fp32 kernel (tiny inputs: fewer points than one 256-point iteration, one slot entirely past the end)
+    n32 = head_net(M, O.init_face_nerf(7), "fp32")
+    with torch.no_grad():
+        r32 = n32.query(rays, z, aud, expr, lat)
+    close(r1, r32, 3e-2 * max(1.0, float(r32.abs().max())), "bf16 vs fp32 raw")
 
 
 def test_to8b_and_video_driver(M):
