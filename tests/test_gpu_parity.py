@@ -1037,3 +1037,29 @@ def test_packed_weights_follow_fused_optimizer_updates(M):
     with torch.no_grad():
         assert torch.equal(after, fresh.query(rays, z, aud, expr, lat)), "inference after training must re-pack"
     assert not torch.equal(before, after)
+
+
+def test_head_torso_composite_bf16_mode(M):
+    """Config 4 in bf16-MLP mode: the four-network head + torso composite against the same networks in fp32 mode (PSNR gate style)."""
+    b = O.synthetic_train_batch(0)
+    n = 96
+    rays, bc = b["rays"][:n], b["bc_rgb"][:n]
+    sds = {"face_nerf_coarse": O.init_face_nerf(11, 64, 79, 32), "face_nerf_fine": O.init_face_nerf(12, 64, 79, 32),
+           "torso_coarse_nerf": O.init_face_nerf(13, 106, 0, 0), "torso_fine_nerf": O.init_face_nerf(14, 106, 0, 0)}
+    gen = torch.Generator().manual_seed(3)
+    aud, expr, lat = torch.randn(64, generator=gen), torch.randn(79, generator=gen), torch.ones(32)
+    pose = torch.eye(4); pose[:3, 3] = torch.tensor([0.02, -0.01, 0.7772])
+    for k in ("torso_coarse_nerf", "torso_fine_nerf", "face_nerf_coarse", "face_nerf_fine"):
+        sds[k] = O.normalise_density(sds[k], rays, aud if "face" in k else torch.randn(106, generator=gen),
+                                     expr if "face" in k else None, lat if "face" in k else None)
+    out = {}
+    for mode in ("fp32", "bf16"):
+        net = M.TorsoNetwork(450, 450, 1200., O.NEAR, O.FAR, 8192, 64, 128, args=M.default_args(dim_aud=64, dim_expr=79, perturb=0., mlp_mode=mode))
+        for k, sd in sds.items():
+            getattr(net, k).load_state_dict(sd)
+        net = net.to(DEV)
+        with torch.no_grad():
+            out[mode] = net(rays.to(DEV), rays.to(DEV), bc.to(DEV), aud.to(DEV), pose.to(DEV), expr.to(DEV), lat.to(DEV))
+    for a, b_ in zip(out["fp32"], out["bf16"]):
+        print(f"head+torso bf16 vs fp32: max-abs {float((a - b_).abs().max()):.3e}  PSNR {_psnr(a, b_):.1f} dB")
+        assert _psnr(a, b_) >= 35.0
