@@ -291,6 +291,13 @@ __device__ __forceinline__ void issue_layer(IssueCtx& c) {
 // ABL (builds with -DINERF_ABLATION only; profiles/ablate_mlp.py): bit 0 = epilogue keeps its barrier protocol but skips the
 // TMEM loads / conversion / smem stores, bit 1 = weights are loaded once (no streaming, no full-barrier waits), bit 2 = the
 // positional-encoding warps skip sincosf, bit 3 = the epilogue skips only its TMEM loads, bit 4 = only its bias/ReLU/convert math.  Outputs are garbage; only the timing is meaningful.
+#ifdef INERF_ABLATION
+__device__ int g_save_abl;      // profiling builds: switch parts of the activation saving off (profiles/ablate_save.py); results are garbage
+#define SAVE_OFF(bit) (g_save_abl & (bit))
+#else
+#define SAVE_OFF(bit) false
+#endif
+
 template <bool TRACE, int ABL = 0, bool SAVE = false>
 __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, int n_steps, int n_rays, float* __restrict__ trace) {
     // Dynamic shared memory is the only shared allocation of this kernel, so it starts at offset 0 of the CTA's
@@ -447,7 +454,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                                 case 10: epi_convert<3, TRACE, SAVE>(r, &packed[c * 16], nullptr, nullptr, s_rw + f0, alpha, rgb0, rgb1, rgb2, tr, dump, neg); break;
                                 default: epi_convert<0, TRACE, SAVE>(r, &packed[c * 16], nullptr, nullptr, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump, neg); break;
                             }
-                            if constexpr (SAVE)      // training: the ReLU mask word of the chunk (the activations follow as a bulk copy of the smem image)
+                            if (SAVE && !SAVE_OFF(1))      // training: the ReLU mask word of the chunk (the activations follow as a bulk copy of the smem image)
                                 a.save_mask[(((size_t)it * 2 + slot) * TRAIN_MASK_WORDS + train_mask_of(l) + (f0 >> 5)) * 128 + row] = ~neg;
                         }
                     }
@@ -455,6 +462,13 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                     if constexpr (TRACE) { const long long q1 = clock64(); te_ld += q1 - q0; q0 = q1; }
                     if (l != 10 || SAVE) {
                         if (h == 0) wait_or_report<TRACE>(&bars->cbar[1], par, 304, l, (int)layer_ctr);
+                        if constexpr (SAVE) {
+                            // training: each warp bulk-copies its own 32 rows of the K-blocks it writes (4 KB per K-block image) to HBM, so no
+                            // barrier couples the warps.  Before overwriting them, lane 0 waits until the copy that last read these rows has
+                            // left shared memory: that is two copies back (this half's K-blocks were written by the same half of the previous
+                            // layer) unless the layer widens (l == 0 after the 128-wide rgb layer), where it is the latest one.
+                            if (lane == 0) { if (h == 0 && l == 0) bulk_wait_read_all(); else bulk_wait_read_but_one(); }
+                        }
                         __syncwarp();      // h1 has finished reading the K-blocks written below
                         if constexpr (TRACE) { const long long q1 = clock64(); te_c1 += q1 - q0; q0 = q1; }
 #pragma unroll
@@ -473,16 +487,12 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                         }
                         fence_proxy_async_smem();
                         if constexpr (SAVE) {
-                            // training: the K-blocks this half just wrote go to HBM as ONE bulk copy of their shared-memory image, issued
-                            // by thread 1 of the slot.  It first waits until its previous copy (the other half's K-blocks) has been read
-                            // out of shared memory, so whoever passes this barrier may overwrite those K-blocks again.
-                            const bool issuer = (row == 1);
-                            if (issuer) bulk_wait_read_all();
-                            named_bar_sync(1 + slot, 128);
-                            if (issuer) {
-                                const int f0h = h * NH;
-                                bulk_s2g(a.save_img + (((size_t)it * 2 + slot) * TRAIN_IMGS + train_img_of(l) + (f0h >> 6)) * 16384,
-                                         act + (f0h >> 6) * 16384, (uint32_t)NH * 256u);      // NH columns = NH/64 K-block images of 16 KB
+                            __syncwarp();
+                            if (lane == 0 && !SAVE_OFF(2)) {
+                                const int kb0 = (h * NH) >> 6, nkb = NH >> 6;      // 2 K-blocks per half (N = 256) or 1 (N = 128)
+                                const uint32_t wrow = (uint32_t)(warp & 3) * 4096u;      // 32 rows = 4 row groups of 1 KB
+                                uint8_t* g = a.save_img + (((size_t)it * 2 + slot) * TRAIN_IMGS + train_img_of(l) + kb0) * 16384 + wrow;
+                                for (int k = 0; k < nkb; ++k) bulk_s2g(g + k * 16384, act + (kb0 + k) * 16384 + wrow, 4096u);
                                 bulk_commit();
                             }
                         }
@@ -508,7 +518,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
             }
         }
         if constexpr (SAVE) {
-            if (row == 1) bulk_wait_all();
+            if (lane == 0) bulk_wait_all();
         }
         if constexpr (TRACE) {
             if (warp == 4 && lane == 0) {
@@ -572,7 +582,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
             }
             fence_proxy_async_smem();
             mbar_arrive(&bars->pe_ready);
-            if constexpr (SAVE) {          // training: gamma(p) is the X operand of dW for pts_linears.0 / .5
+            if (SAVE && !SAVE_OFF(4)) {          // training: gamma(p) is the X operand of dW for pts_linears.0 / .5
 #pragma unroll
                 for (int sl = 0; sl < 2; ++sl) {
                     uint8_t* dst = a.save_img + (((size_t)it * 2 + sl) * TRAIN_IMGS + TRAIN_IMG_PE) * 16384 + (t >> 3) * 1024 + (t & 7) * 128;
@@ -607,7 +617,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
 #pragma unroll
                     for (int j = 0; j < 27; ++j) enc[j] = 0.f;
                 }
-                if constexpr (SAVE) {      // training: gamma(v) per POINT, the X operand of dW for the view columns of views_linears.0
+                if (SAVE && !SAVE_OFF(4)) {      // training: gamma(v) per POINT, the X operand of dW for the view columns of views_linears.0
 #pragma unroll
                     for (int sl = 0; sl < 2; ++sl) {
                         long long p = it * 256 + sl * 128 + t, pfirst = it * 256 + sl * 128;
@@ -809,7 +819,7 @@ int mlp_bf16_launch(const MlpArgs& a, bool embedded, cudaStream_t st) {
         if (g_hang_host) for (int i = 0; i < 8; ++i) g_hang_host[i] = 0;
     }
 #ifdef INERF_ABLATION
-    if (const char* e = getenv("INERF_ABL")) {
+    if (const char* e = a.save_img ? nullptr : getenv("INERF_ABL")) {
         const int abl = atoi(e);
 #define ABL_CASE(N_) case N_: cudaFuncSetAttribute(mlp_bf16_kernel<false, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC); \
                               mlp_bf16_kernel<false, N_><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, nullptr); break;
@@ -827,6 +837,19 @@ int mlp_bf16_launch(const MlpArgs& a, bool embedded, cudaStream_t st) {
             if (e != cudaSuccess) { set_error("mlp_bf16: setup: %s", cudaGetErrorString(e)); return (int)e; }
             save_dev = dev;
         }
+#ifdef INERF_ABLATION
+        { const char* e = getenv("INERF_SAVE_ABL"); const int v = e ? atoi(e) : 0; cudaMemcpyToSymbolAsync(g_save_abl, &v, sizeof(v), 0, cudaMemcpyHostToDevice, st); cudaStreamSynchronize(st); }
+        if (const char* e = getenv("INERF_ABL")) {      // weight streaming (2) / sincosf (4) off on top of the saving switches
+            const int abl = atoi(e);
+            if (abl == 2 || abl == 4) {
+                if (abl == 2) { cudaFuncSetAttribute(mlp_bf16_kernel<false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+                                mlp_bf16_kernel<false, 2, true><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, nullptr); }
+                else { cudaFuncSetAttribute(mlp_bf16_kernel<false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+                       mlp_bf16_kernel<false, 4, true><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, nullptr); }
+                return check_launch("inerf_mlp_fwd_train[bf16,ablation]");
+            }
+        }
+#endif
         mlp_bf16_kernel<false, 0, true><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, nullptr);
         return check_launch("inerf_mlp_fwd_train[bf16]");
     }

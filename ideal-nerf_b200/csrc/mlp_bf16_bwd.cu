@@ -266,6 +266,10 @@ __global__ void __launch_bounds__(NTH, 1) mlp_bf16_bwd_chain_kernel(BwdChainArgs
                         }
                     } else {
                         if (h == 0) bwait(&bars->cbar[1], par);
+                        // the delta image for dW: each warp bulk-copies its own 32 rows of the K-blocks it writes (4 KB per K-block image), so no
+                        // barrier couples the warps.  Before overwriting them lane 0 waits until the copy that last read these rows has left
+                        // shared memory: two copies back (same half of the previous layer), or the latest where the layer widens (j == 2).
+                        if (lane == 0) { if (h == 0 && j == 2) bulk_wait_read_all(); else bulk_wait_read_but_one(); }
                         __syncwarp();
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
@@ -280,15 +284,15 @@ __global__ void __launch_bounds__(NTH, 1) mlp_bf16_bwd_chain_kernel(BwdChainArgs
                             }
                         }
                         fence_proxy_async_smem();
-                        // the delta image for dW: ONE bulk copy of the K-blocks this half just wrote (their shared-memory image), issued by
-                        // thread 1 of the slot once its previous copy has been read out (so those K-blocks may be overwritten again)
-                        const bool issuer = (row == 1);
-                        if (issuer) bulk_wait_read_all();
-                        named_bar_sync(1 + slot, 128);
-                        if (issuer) {
-                            const int f0h = h * NH;
-                            bulk_s2g(gimg_base + (f0h >> 6) * 16384, act + (f0h >> 6) * 16384, (uint32_t)NH * 256u);      // NH columns = NH/64 K-block images of 16 KB
+                        __syncwarp();
+                        if (lane == 0) {
+                            const int kb0 = (h * NH) >> 6, nkb = NH >> 6;
+                            const uint32_t wrow = (uint32_t)(warp & 3) * 4096u;
+                            for (int k = 0; k < nkb; ++k) bulk_s2g(gimg_base + (kb0 + k) * 16384 + wrow, act + (kb0 + k) * 16384 + wrow, 4096u);
                             bulk_commit();
+                            // last copy of the iteration: the init warps refill K-blocks 0,1 once the final layer's MMAs are done, so the copy
+                            // of those K-blocks (the previous half's) must have left shared memory before this half releases that layer
+                            if (j == NLAY - 2 && h == 1) bulk_wait_read_but_one();
                         }
                     }
                     __syncwarp();
@@ -296,7 +300,7 @@ __global__ void __launch_bounds__(NTH, 1) mlp_bf16_bwd_chain_kernel(BwdChainArgs
                 }
             }
         }
-        if (row == 1) bulk_wait_all();
+        if (lane == 0) bulk_wait_all();
     } else if (warp >= 12) {
         // ================= init: d_raw -> d_v2, d_sigma tile, d_raw image ==================================================
         // Phase 1 (any time): d_v2 and the d_raw image of row t of both slots go to HBM (the dW kernel needs them there anyway).

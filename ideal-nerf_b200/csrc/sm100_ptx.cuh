@@ -52,6 +52,8 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // every bulk group of this thread has finished READING its shared-memory source (the source may be overwritten)
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the most recent bulk group of this thread have finished reading their shared-memory source
+__device__ __forceinline__ void bulk_wait_read_but_one() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 // every bulk group of this thread has completed (writes performed)
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // named barrier over `nthreads` threads of the CTA (id 0 is __syncthreads)
