@@ -109,6 +109,37 @@ def cpu_reference_rays_per_s(n_rays, steps, warmup):
     return n_rays / dt, dt, torch.get_num_threads()
 
 
+def torch_gpu_port_rays_per_s(dev):
+    """The same oracle port in stock PyTorch eager fp32 ON THE GPU (what the reference does after set_default_tensor_type(cuda),
+    audio_exp_nerf.py:598): one 450x450 frame in 25 chunks of 8192 rays (the reference's batchify_rays chunk).  Part of the baseline
+    leg: a reported context number next to the CPU one, never on the product path."""
+    from oracle import render_oracle as O
+    fr = O.synthetic_frame(0)
+    c, f = O.init_face_nerf(1), O.init_face_nerf(2)
+    to = lambda t: t.to(dev)
+    c, f = {k: to(v) for k, v in c.items()}, {k: to(v) for k, v in f.items()}
+    rays, bc, aud, expr, lat = to(fr["rays"]), to(fr["bc_rgb"]), to(fr["aud"]), to(fr["expr"]), to(fr["latent"])
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+
+    def frame():
+        for i in range(0, N_RAYS, 8192):
+            O.render_rays(rays[i:i + 8192], bc[i:i + 8192], c, f, aud, expr, lat)
+
+    with torch.device(dev), torch.no_grad():
+        frame()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            frame()
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / 2
+    return {"value": N_RAYS / (ms * 1e-3), "unit": "rays/s", "ms_per_frame": ms, "kind": "port",
+            "sample": f"full 202500-ray frame in 25 chunks of 8192, 1 warm-up + 2 timed frames, torch {torch.__version__} eager fp32 "
+                      f"(allow_tf32={tf32}) on the same GPU"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -211,9 +242,23 @@ def train_step_bench(M, dev, steps, mode="bf16"):
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    return {"rays_per_s": 3072 / (ms * 1e-3), "ms_per_step": ms, "n_rand": 3072, "mlp_mode": mode, "optimizer": "Adam lr=3e-4",
-            "loss": float(loss.detach()), "gpu_launches_per_step": ops.LAUNCHES["count"] / steps,
-            "kernels_ms_per_step": {k: round(v[1] / steps, 3) for k, v in kt.summary().items()}}
+    kms = {k: v[1] / steps for k, v in kt.summary().items()}
+    out = {"rays_per_s": 3072 / (ms * 1e-3), "ms_per_step": ms, "n_rand": 3072, "mlp_mode": mode, "optimizer": "Adam lr=3e-4",
+           "loss": float(loss.detach()), "gpu_launches_per_step": ops.LAUNCHES["count"] / steps,
+           "kernels_ms_per_step": {k: round(v, 3) for k, v in kms.items()}}
+    if mode == "bf16":
+        # The three training kernels exchange their operands through HBM, so HBM bounds them.  Algorithmic bytes per
+        # 128-point tile: forward writes 40 activation images (16 KB) + 76 mask words x 128 rows; the chain reads the masks and writes 39
+        # delta images; dW reads every activation and delta image once.
+        tiles = 3072 * (S1 + S1 + S_IMP) // 128
+        per_tile = (40 + 39 + 79) * 16384 + 2 * 76 * 512
+        t_k = (kms.get("inerf_mlp_fwd_train", 0.0) + kms.get("inerf_mlp_bwd", 0.0)) * 1e-3
+        pk, pk_kind = peaks()
+        if t_k > 0:
+            ach = tiles * per_tile / t_k / 1e9
+            out["roofline"] = {"bound": "hbm", "kernels": "inerf_mlp_fwd_train + inerf_mlp_bwd (chain + dW)", "achieved": ach, "peak": pk["hbm_gbs"],
+                               "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "bytes_per_step": tiles * per_tile, "peak_kind": f"HBM copy, {pk_kind}"}
+    return out
 
 
 def run_ours(args):
@@ -350,6 +395,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
                                     "sample": f"3072 of 202500 frame rays, 1 warm-up + 2 timed runs ({dt:.2f} s each), "
                                               f"torch {torch.__version__} fp32 {torch.backends.cpu.get_cpu_capability()}"}
+            line["torch_gpu_baseline"] = torch_gpu_port_rays_per_s(dev)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
