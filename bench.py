@@ -52,25 +52,51 @@ def mlp_traffic():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md recipe): NVML polled every 10 ms through pynvml when it
+    loads (the timed region of a default run is a quarter of a second), else one nvidia-smi query per 0.2 s."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll_nvml(self):
+        n, h = self.nvml, self.handle
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        self.rows.append([str(sm), str(mx), ""] + ["Active" if mask & b else "Not Active" for _, b in
+                                                   (self.BITS[1], self.BITS[3], self.BITS[2], self.BITS[0])])
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 7:
-                    self.rows.append(f)
+                if self.nvml is not None:
+                    self._poll_nvml()
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    f = [x.strip() for x in out.strip().split(",")]
+                    if len(f) >= 7:
+                        self.rows.append(f)
             except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+                if self.nvml is not None:
+                    self.nvml = None              # fall back to nvidia-smi for the rest of the run
+            self._stop_evt.wait(0.01 if self.nvml is not None else 0.2)
 
     def stop(self):
         self._stop_evt.set()
@@ -83,7 +109,7 @@ class ClockSampler(threading.Thread):
                     reasons.add(name)
         mx = [float(r[1]) for r in self.rows if r[1].replace('.', '', 1).isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -316,7 +316,7 @@ __global__ void fold_cond_kernel(FoldArgs f) {
         const float* B = f.w[2 * b + 1];
         const int ldw = (b == 0) ? 63 + C : (b == 5 ? 319 + C : 256);
         const bool folded = (b == 0 || b == 5) && C > 0;
-        for (int n = warp; n < 256; n += nwarp) {
+        for (int n = blockIdx.y * 32 + warp; n < blockIdx.y * 32 + 32; n += nwarp) {      // grid.y = 8 row groups: the rows are independent
             float s = 0.f;
             if (folded)
                 for (int j = lane; j < C; j += 32) s = fmaf(W[(size_t)n * ldw + 63 + j], c[j], s);
@@ -331,7 +331,7 @@ __global__ void fold_cond_kernel(FoldArgs f) {
         const float* W = f.w[P_VIEWS_W + 2 * v];
         const float* B = f.w[P_VIEWS_W + 2 * v + 1];
         const int ldw = 283 + f.de;
-        for (int n = warp; n < 128; n += nwarp) {
+        for (int n = blockIdx.y * 16 + warp; n < blockIdx.y * 16 + 16; n += nwarp) {
             float s = 0.f;
             if (v == 0)
                 for (int j = lane; j < f.de; j += 32) s = fmaf(W[(size_t)n * ldw + 283 + j], c[f.da + j], s);
@@ -341,7 +341,7 @@ __global__ void fold_cond_kernel(FoldArgs f) {
                 write_bias_tile_row(tiles + 65536 + (2 * v + (n >> 6)) * 2048, n & 63, B[n] + s);
             }
         }
-    } else if (threadIdx.x < 4) {
+    } else if (threadIdx.x < 4 && blockIdx.y == 0) {
         f.cond[cl.alpha_b() + threadIdx.x] = threadIdx.x == 0 ? f.w[P_ALPHA_B][0] : f.w[P_RGB_B][threadIdx.x - 1];
     }
 }
@@ -410,7 +410,7 @@ extern "C" int inerf_mlp_fold_cond(const InerfNetDims* dims, const float* const*
     f.aud = aud; f.expr = expr; f.latent = latent;
     f.da = dims->dim_aud; f.de = dims->dim_expr; f.dl = dims->dim_latent;
     f.cond = cond;
-    fold_cond_kernel<<<12, 256, 0, as_stream(stream)>>>(f);
+    fold_cond_kernel<<<dim3(12, 8), 256, 0, as_stream(stream)>>>(f);
     return check_launch("inerf_mlp_fold_cond");
 }
 
