@@ -229,35 +229,42 @@ def composite_standalone(M, dev, n_rays, reps=20):
     return tot_bytes, tot_ms
 
 
-def train_step_bench(M, dev, steps, mode="bf16"):
+def train_step_bench(M, dev, steps, mode="bf16", rank=0, world=1):
     """BASELINE.json config 3: N_rand=3072 rays (64+128 samples), loss of audio_exp_nerf.py:540-548, backward through
-    compositing + both FaceNeRFs, Adam(lr=3e-4) step.  mode: bf16 = tcgen05 forward-with-save + chain + dW kernels; fp32 = FFMA."""
-    from ideal_nerf_b200 import synthetic as S, ops
+    compositing + both FaceNeRFs, Adam(lr=3e-4) step.  mode: bf16 = tcgen05 forward-with-save + chain + dW kernels; fp32 = FFMA.
+    world > 1: data parallel, weak scaling -- every rank takes its own 3072 rays through identical weights, one NCCL all-reduce of the
+    flattened gradients (frame.allreduce_grads, the reference's nn.DataParallel backward) before the optimiser step; time = max over ranks."""
+    import torch.distributed as dist
+    from ideal_nerf_b200 import synthetic as S, ops, frame as FR
     cam, fr = S.camera(), S.frame_inputs(0)
     a = M.default_args(dim_aud=64, dim_expr=76, perturb=1.0, mlp_mode=mode, N_samples=S1, N_importance=S_IMP)
     net = M.Network(H, W, cam["focal"], S.NEAR, S.FAR, 8192, None, S1, S_IMP, args=a)
     torch.manual_seed(4321)
     net.apply(M.init_weights)
     net = net.to(dev).train()
-    g = torch.Generator().manual_seed(5)
+    g = torch.Generator().manual_seed(5 + rank)
     idx = torch.randperm(N_RAYS, generator=g)[:3072].to(dev)
     rays = ops.get_rays_packed(H, W, cam["focal"], cam["c2w"].to(dev), S.NEAR, S.FAR)[idx].contiguous()
     bc, tgt = fr["bc_rgb"].to(dev)[idx].contiguous(), torch.rand(3072, 3, generator=g).to(dev)
     aud, expr = fr["aud"].to(dev), fr["expr"].to(dev)
     lat = torch.ones(32, device=dev, requires_grad=True)
     from ideal_nerf_b200 import train as T
-    opt = torch.optim.Adam(list(net.parameters()) + [lat], lr=3e-4, betas=(0.9, 0.999), fused=True)
+    params = list(net.parameters()) + [lat]
+    opt = torch.optim.Adam(params, lr=3e-4, betas=(0.9, 0.999), fused=True)
 
     def step():
         opt.zero_grad(set_to_none=True)
         r = net.render_rays(rays, bc, aud, None, lat, expr)
         loss = T.head_loss(r, tgt, lat, 0.0005)[0]            # mse(rgb) + mse(rgb0) + 10 * lc_weight * ||latent||  (:540-548)
         loss.backward()
+        FR.allreduce_grads(params, world)
         opt.step()
         return loss
 
     for _ in range(2):
         step()
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ops.LAUNCHES["count"] = 0
@@ -266,10 +273,15 @@ def train_step_bench(M, dev, steps, mode="bf16"):
         for _ in range(steps):
             loss = step()
         e1.record()
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
     kms = {k: v[1] / steps for k, v in kt.summary().items()}
-    out = {"rays_per_s": 3072 / (ms * 1e-3), "ms_per_step": ms, "n_rand": 3072, "mlp_mode": mode, "optimizer": "Adam lr=3e-4",
+    out = {"rays_per_s": 3072 * world / (ms * 1e-3), "ms_per_step": ms, "n_rand": 3072 * world, "n_gpus": world, "mlp_mode": mode, "optimizer": "Adam lr=3e-4",
            "loss": float(loss.detach()), "gpu_launches_per_step": ops.LAUNCHES["count"] / steps,
            "kernels_ms_per_step": {k: round(v, 3) for k, v in kms.items()}}
     if mode == "bf16":
@@ -377,6 +389,8 @@ def run_ours(args):
     value = rays_per_step * args.steps / (total_ms * 1e-3)
     e2e_value = rays_per_step * args.steps / (t_e2e * 1e-3)
 
+    train_bf16 = None if args.no_train else train_step_bench(M, dev, 5, "bf16", rank, world)      # every rank takes part (gradient all-reduce)
+
     if rank == 0:
         pk, pk_kind = peaks()
         n_mlp, mlp_ms = ksum.get("inerf_mlp_fwd", (0, 0.0))
@@ -413,8 +427,9 @@ def run_ours(args):
                                                "kernel_ms_total": cmp_ms, "note": "one event pair per 0.1 ms launch: includes event overhead"}},
             "kernels_ms": {k: round(v[1], 3) for k, v in ksum.items()},
         }
+        if train_bf16 is not None:
+            line["train_step"] = train_bf16
         if world == 1 and not args.no_train:
-            line["train_step"] = train_step_bench(M, dev, 5, "bf16")
             line["train_step_fp32"] = train_step_bench(M, dev, 3, "fp32")
         if world == 1 and not args.no_cpu_baseline:
             v, dt, cores = cpu_reference_rays_per_s(3072, 2, 1)
