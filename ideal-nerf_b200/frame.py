@@ -81,11 +81,12 @@ def allreduce_grads(parameters, world, group=None):
     ps = [p for p in parameters if p.grad is not None]
     if world == 1 or not ps:
         return
-    flat = torch.cat([p.grad.reshape(-1) for p in ps])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    flat.div_(world)
-    o = 0
-    for p in ps:
-        n = p.grad.numel()
-        p.grad.copy_(flat[o:o + n].view_as(p.grad))
-        o += n
+    grads = [p.grad for p in ps]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)          # the division happens inside the collective
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+    # one multi-tensor copy back instead of a launch per parameter (the step is ~5 ms: 50 tiny launches would show)
+    torch._foreach_copy_(grads, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)])
