@@ -245,7 +245,7 @@ __device__ __forceinline__ void issue_layer(IssueCtx& c) {
                     if (i == KB_PER_HALF_PREV) wait_or_report<TRACE>(&bars->ebar[1], par_prev, 202, L, (int)c.layer_ctr);
                 }
             }
-            if constexpr (TRACE) { const long long c1 = clock64(); c.t_e += c1 - c0; c.t_e_layer[L] += c1 - c0; c0 = c1; }
+            if constexpr (TRACE) { const long long c1 = clock64(); c.t_e += c1 - c0; c.t_e_layer[c.layer_ctr % 11] += c1 - c0; c0 = c1; }
             if (L == 0 && h == 0 && i == 0) wait_or_report<TRACE>(&bars->pe_ready, c.iter_ctr & 1, 203, L, (int)c.iter_ctr);
             if constexpr (TRACE) { const long long c1 = clock64(); c.t_pe += c1 - c0; c0 = c1; }
             if (!(ABL & 2) || (c.layer_ctr == 0 && L == 0 && h * CNT + i < NSTAGE))
@@ -384,9 +384,19 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
         for (int j = 0; j < 11; ++j) c.t_e_layer[j] = 0;
         const long long t_tot = clock64();
         for (long long it = blockIdx.x; it < n_iter; it += gridDim.x, ++c.iter_ctr) {
-            issue_layer<0, TRACE, ABL>(c); issue_layer<1, TRACE, ABL>(c); issue_layer<2, TRACE, ABL>(c); issue_layer<3, TRACE, ABL>(c);
-            issue_layer<4, TRACE, ABL>(c); issue_layer<5, TRACE, ABL>(c); issue_layer<6, TRACE, ABL>(c); issue_layer<7, TRACE, ABL>(c);
-            issue_layer<8, TRACE, ABL>(c); issue_layer<9, TRACE, ABL>(c); issue_layer<10, TRACE, ABL>(c);
+            // Layers of equal geometry share ONE copy of the straight-line issue code (L1-L4, L6, L7 are 256 x 256 after a 256-wide
+            // layer; V1, V2 are 128 x 128 after a 128-wide one): 11 inlined copies were 78 KB of SASS streamed once per iteration, which
+            // together with the epilogue and PE code overflowed the instruction cache the epilogue warps live in (ncu: stall_no_inst).
+            issue_layer<0, TRACE, ABL>(c);
+#pragma unroll 1
+            for (int seg = 0; seg < 2; ++seg) {
+#pragma unroll 1
+                for (int r = 0; r < (seg ? 2 : 4); ++r) issue_layer<1, TRACE, ABL>(c);
+                if (seg == 0) issue_layer<5, TRACE, ABL>(c);
+            }
+            issue_layer<8, TRACE, ABL>(c);
+#pragma unroll 1
+            for (int r = 0; r < 2; ++r) issue_layer<9, TRACE, ABL>(c);
         }
         if constexpr (TRACE) {      // per-CTA issuer timing after the activation trace: {total, wait E, wait PE, wait weights, iterations}
             if (lane == 0) {

@@ -206,8 +206,12 @@ __global__ void __launch_bounds__(NTH, 1) mlp_bf16_bwd_chain_kernel(BwdChainArgs
         c.tmem_base = tmem_base;
         c.stage = 0; c.wpar = 0; c.layer_ctr = 0; c.iter_ctr = 0;
         for (long long it = blockIdx.x; it < n_iter; it += gridDim.x, ++c.iter_ctr) {
-            issue_layer<0>(c); issue_layer<1>(c); issue_layer<2>(c); issue_layer<3>(c); issue_layer<4>(c);
-            issue_layer<5>(c); issue_layer<6>(c); issue_layer<7>(c); issue_layer<8>(c); issue_layer<9>(c);
+            // layers 3..8 have the same geometry (256 x 256 after a 256-wide layer): one copy of the issue code, run six times,
+            // keeps the kernel's SASS inside the instruction cache (see the forward kernel)
+            issue_layer<0>(c); issue_layer<1>(c); issue_layer<2>(c);
+#pragma unroll 1
+            for (int r = 0; r < 6; ++r) issue_layer<3>(c);
+            issue_layer<9>(c);
         }
     } else if (warp >= 4 && warp < 12) {
         // ================= epilogue: one row per thread ==================================================================
