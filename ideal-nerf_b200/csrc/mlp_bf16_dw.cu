@@ -163,19 +163,31 @@ __global__ void __launch_bounds__(DW_THREADS, 1) mlp_bf16_dw_kernel(const DwArgs
             const int row = q * 32 + lane;
             bounded_wait(&bars->done, n_done & 1);
             tc_fence_after();
-            const bool row_ok = row >= t.row_lo && row < t.row_hi;
-            float* G = a.g[t.w_index] + (size_t)(t.out_row0 + row - t.row_lo) * t.ldw + t.wcol;
+            // The accumulator arrives one ROW per lane; reducing it into the gradient from there would make every red.add touch 32
+            // different rows (32 sectors per instruction, ~20 us per work item).  So each warp first parks its 32 rows in the (now idle)
+            // stage buffers -- [32][N + 4] fp32, the 16-byte pad keeps the 128-bit stores of 8 consecutive rows on distinct banks --
+            // and then walks them row by row with the lanes across 32 consecutive columns: fully coalesced reductions.
+            float* park = reinterpret_cast<float*>(sm) + (size_t)q * 32 * (256 + 4);
+            const int ldp = N + 4;
             const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
             for (int c0 = 0; c0 < N; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(t_lane + c0, r);
                 tmem_wait_ld();
-                if (row_ok) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (c0 + j < t.kvalid) atomicAdd(G + c0 + j, __uint_as_float(r[j]));
-                }
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<uint4*>(park + lane * ldp + c0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
             }
+            __syncwarp();
+            for (int rr = 0; rr < 32; ++rr) {
+                const int orow = q * 32 + rr;
+                if (orow < t.row_lo || orow >= t.row_hi) continue;      // warp-uniform
+                float* G = a.g[t.w_index] + (size_t)(t.out_row0 + orow - t.row_lo) * t.ldw + t.wcol;
+                const float* src = park + rr * ldp;
+                for (int c0 = 0; c0 < N; c0 += 32)
+                    if (c0 + lane < t.kvalid) atomicAdd(G + c0 + lane, src[c0 + lane]);
+            }
+            const bool row_ok = row >= t.row_lo && row < t.row_hi;
             if (t.bias_index >= 0) {
                 uint32_t r[32];
                 tmem_ld32(t_lane + 256, r);          // 16 valid columns, all equal to the column sum; read 32 (allocated) and use [0]
@@ -183,6 +195,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) mlp_bf16_dw_kernel(const DwArgs
                 if (row_ok) atomicAdd(a.g[t.bias_index] + t.out_row0 + row - t.row_lo, __uint_as_float(r[0]));
             }
             tc_fence_before();
+            fence_proxy_async_smem();      // the parked rows were generic-proxy accesses to buffers the next bulk loads (async proxy) overwrite
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->drained);
         }
