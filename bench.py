@@ -267,18 +267,22 @@ def train_step_bench(M, dev, steps, mode="bf16", rank=0, world=1):
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ops.LAUNCHES["count"] = 0
-    with ops.kernel_timing() as kt:
-        e0.record()
-        for _ in range(steps):
-            loss = step()
-        e1.record()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # per-kernel breakdown in a second pass: an event pair around each of the 17 launches of a 4.5 ms step would cost the step ~4 %
+    ops.LAUNCHES["count"] = 0
+    with ops.kernel_timing() as kt:
+        for _ in range(steps):
+            step()
+        torch.cuda.synchronize()
     ms = float(t.item())
     kms = {k: v[1] / steps for k, v in kt.summary().items()}
     out = {"rays_per_s": 3072 * world / (ms * 1e-3), "ms_per_step": ms, "n_rand": 3072 * world, "n_gpus": world, "mlp_mode": mode, "optimizer": "Adam lr=3e-4",
