@@ -233,9 +233,9 @@ def train_step_bench(M, dev, steps, mode="bf16", rank=0, world=1):
     """BASELINE.json config 3: N_rand=3072 rays (64+128 samples), loss of audio_exp_nerf.py:540-548, backward through
     compositing + both FaceNeRFs, Adam(lr=3e-4) step.  mode: bf16 = tcgen05 forward-with-save + chain + dW kernels; fp32 = FFMA.
     world > 1: data parallel, weak scaling -- every rank takes its own 3072 rays through identical weights, one NCCL all-reduce of the
-    flattened gradients (frame.allreduce_grads, the reference's nn.DataParallel backward) before the optimiser step; time = max over ranks."""
+    flat gradient (train.FlatParams.gather_grads, the reference's nn.DataParallel backward) before the optimiser step; time = max over ranks."""
     import torch.distributed as dist
-    from ideal_nerf_b200 import synthetic as S, ops, frame as FR
+    from ideal_nerf_b200 import synthetic as S, ops
     cam, fr = S.camera(), S.frame_inputs(0)
     a = M.default_args(dim_aud=64, dim_expr=76, perturb=1.0, mlp_mode=mode, N_samples=S1, N_importance=S_IMP)
     net = M.Network(H, W, cam["focal"], S.NEAR, S.FAR, 8192, None, S1, S_IMP, args=a)
@@ -250,14 +250,16 @@ def train_step_bench(M, dev, steps, mode="bf16", rank=0, world=1):
     lat = torch.ones(32, device=dev, requires_grad=True)
     from ideal_nerf_b200 import train as T
     params = list(net.parameters()) + [lat]
-    opt = torch.optim.Adam(params, lr=3e-4, betas=(0.9, 0.999), fused=True)
+    flat = T.FlatParams(params)                               # train.TrainStep's optimiser set-up: every parameter a view of one buffer
+    opt = torch.optim.Adam([flat.flat], lr=3e-4, betas=(0.9, 0.999), fused=True)
 
     def step():
-        opt.zero_grad(set_to_none=True)
+        for p in params:
+            p.grad = None
         r = net.render_rays(rays, bc, aud, None, lat, expr)
         loss = T.head_loss(r, tgt, lat, 0.0005)[0]            # mse(rgb) + mse(rgb0) + 10 * lc_weight * ||latent||  (:540-548)
         loss.backward()
-        FR.allreduce_grads(params, world)
+        flat.gather_grads(world)                              # + the gradient all-reduce when world > 1
         opt.step()
         return loss
 

@@ -147,3 +147,31 @@ def test_network_state_dict_matches_reference_keys_and_checkpoint_round_trip(M, 
     assert torch.equal(net2.face_nerf_coarse.pts_linears[0].weight, before)                      # dropped key: untouched
     assert torch.equal(net2.face_nerf_coarse.pts_linears[1].weight, src.face_nerf_coarse.pts_linears[1].weight)
     assert torch.equal(net2.aud_net.encoder_conv[0].weight, src.aud_net.encoder_conv[0].weight)
+
+
+def test_flat_params_adam_equals_per_parameter_adam():
+    """train.FlatParams: one-tensor Adam over the re-homed parameters == torch.optim.Adam over the separate parameters (audio_exp_nerf.py:529,
+    the reference's optimiser), including a parameter that never receives a gradient; views stay 256-byte aligned and live."""
+    import torch
+    from ideal_nerf_b200.train import FlatParams
+    torch.manual_seed(3)
+    mk = lambda: torch.nn.ModuleList([torch.nn.Linear(7, 5), torch.nn.Linear(5, 3), torch.nn.Linear(3, 3)])     # the last one is never used
+    a, b = mk(), mk()
+    b.load_state_dict(a.state_dict())
+    opt_a = torch.optim.Adam(a.parameters(), lr=1e-2)
+    fp = FlatParams(list(b.parameters()))
+    opt_b = torch.optim.Adam([fp.flat], lr=1e-2)
+    for p in b.parameters():
+        assert p.data_ptr() % 256 == fp.flat.data_ptr() % 256 and p.is_contiguous()
+    x = torch.randn(11, 7)
+    for _ in range(4):
+        opt_a.zero_grad(set_to_none=True)
+        a[1](torch.relu(a[0](x))).square().mean().backward()
+        opt_a.step()
+        for p in b.parameters():
+            p.grad = None
+        b[1](torch.relu(b[0](x))).square().mean().backward()
+        fp.gather_grads()
+        opt_b.step()
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(pa, pb, rtol=0, atol=1e-7), float((pa - pb).abs().max())

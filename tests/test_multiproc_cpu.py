@@ -90,3 +90,44 @@ def test_allreduce_grads_world2_gloo_matches_full_batch():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert q.get(timeout=10) <= 1e-6
+
+
+def _flat_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ideal_nerf_b200.frame import band
+    from ideal_nerf_b200.train import FlatParams
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3))
+    ref = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3))
+    ref.load_state_dict(net.state_dict())
+    fp = FlatParams(list(net.parameters()))
+    opt, opt_ref = torch.optim.Adam([fp.flat], lr=1e-2), torch.optim.Adam(ref.parameters(), lr=1e-2)
+    x, y = torch.randn(3072, 5), torch.randn(3072, 3)
+    lo, hi = band(3072, rank, world)
+    for _ in range(3):
+        for p in net.parameters():
+            p.grad = None
+        torch.mean((net(x[lo:hi]) - y[lo:hi]) ** 2).backward()
+        fp.gather_grads(world)
+        opt.step()
+        opt_ref.zero_grad(set_to_none=True)
+        torch.mean((ref(x) - y) ** 2).backward()
+        opt_ref.step()
+    if rank == 0:
+        q.put(max(float((a - b).abs().max()) for a, b in zip(net.parameters(), ref.parameters())))
+    dist.destroy_process_group()
+
+
+def test_flat_params_data_parallel_adam_world2_gloo():
+    """train.FlatParams: 2 ranks x half the batch, all-reduce of the flat gradient, one-tensor Adam == single-process Adam on the full batch."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_flat_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) <= 1e-5
