@@ -181,7 +181,7 @@ def run_reference(args):
                              "sample": f"{n} of 202500 frame rays per step, torch {torch.__version__} fp32, "
                                        f"{torch.backends.cpu.get_cpu_capability()}"},
             "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -443,12 +443,28 @@ def run_ours(args):
                                     "sample": f"3072 of 202500 frame rays, 1 warm-up + 2 timed runs ({dt:.2f} s each), "
                                               f"torch {torch.__version__} fp32 {torch.backends.cpu.get_cpu_capability()}"}
             line["torch_gpu_baseline"] = torch_gpu_port_rays_per_s(dev)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # Libraries print to fd 1 as well (NCCL's version banner on the first collective, for one): keep a private handle on the original
+    # stdout for the result line and point fd 1 at stderr, so that stdout carries exactly one line whatever else talks.
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
