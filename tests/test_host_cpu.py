@@ -175,3 +175,23 @@ def test_flat_params_adam_equals_per_parameter_adam():
         opt_b.step()
     for pa, pb in zip(a.parameters(), b.parameters()):
         assert torch.allclose(pa, pb, rtol=0, atol=1e-7), float((pa - pb).abs().max())
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the oracle port on the host cores) honours the driver's contract without a GPU: exactly one stdout
+    line, the metric / unit / config of the product arm, impl = reference, a cpu_baseline and an e2e object of its own."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-400:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:400]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "rays/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["metric"].startswith("rays/sec render") and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
