@@ -466,6 +466,16 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                             }
                             if (SAVE && !SAVE_OFF(1))      // training: the ReLU mask word of the chunk (the activations follow as a bulk copy of the smem image)
                                 a.save_mask[(((size_t)it * 2 + slot) * TRAIN_MASK_WORDS + train_mask_of(l) + (f0 >> 5)) * 128 + row] = ~neg;
+                            if (!SAVE && h == 1 && l != 10) {
+                                // second half: nothing reads these K-blocks any more (its own MMAs are complete), so each chunk goes to shared
+                                // memory as soon as it is converted and drains behind the next chunk's load instead of in front of the fence
+                                uint8_t* kb = act + (f0 >> 6) * 16384 + row_off;
+                                const int ch0 = (f0 & 63) >> 3;
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    *reinterpret_cast<uint4*>(kb + (((ch0 + q) ^ rsw) << 4)) =
+                                        make_uint4(packed[c * 16 + q * 4], packed[c * 16 + q * 4 + 1], packed[c * 16 + q * 4 + 2], packed[c * 16 + q * 4 + 3]);
+                            }
                         }
                     }
                     tc_fence_before();
@@ -483,7 +493,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                         if constexpr (TRACE) { const long long q1 = clock64(); te_c1 += q1 - q0; q0 = q1; }
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
-                            if (c < nchunk && !(ABL & 1)) {
+                            if (c < nchunk && !(ABL & 1) && (SAVE || h == 0)) {
                                 const int f0 = h * NH + c * 32;
                                 uint8_t* kb = act + (f0 >> 6) * 16384 + row_off;
                                 const int ch0 = (f0 & 63) >> 3;                // first 16-byte chunk inside the 128-byte row
