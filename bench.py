@@ -115,7 +115,14 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port of the reference algorithm on the host cores
 # ------------------------------------------------------------------------------------------------
+def _reference_available():
+    from oracle import ref_import
+    return ref_import.available()
+
+
 def cpu_reference_rays_per_s(n_rays, steps, warmup):
+    """The reference's own Network.render_rays (oracle/_ref: the verbatim copy oracle/make_ref.py made, or /root/reference in the build
+    container) on the host cores; the oracle port when neither exists.  Returns (rays/s, s per run, threads, kind)."""
     from oracle import render_oracle as O
     torch.set_num_threads(os.cpu_count())
     fr = O.synthetic_frame(0)
@@ -124,34 +131,55 @@ def cpu_reference_rays_per_s(n_rays, steps, warmup):
     rays, bc = fr["rays"][sub].contiguous(), fr["bc_rgb"][sub].contiguous()
     c = O.normalise_density(c, rays, fr["aud"], fr["expr"], fr["latent"])
     f = O.normalise_density(f, rays, fr["aud"], fr["expr"], fr["latent"])
+    kind = "port"
+    run = lambda: O.render_rays(rays, bc, c, f, fr["aud"], fr["expr"], fr["latent"])
+    if _reference_available():
+        from oracle import ref_import
+        head = ref_import.import_head(perturb=1.0, force_cpu=True)          # unmodified reference, its hard-coded .cuda() kept on the host
+        net = head.Network(H, W, 1200., O.NEAR, O.FAR, 8192, None, S1, S_IMP)
+        net.face_nerf_coarse.load_state_dict(c)
+        net.face_nerf_fine.load_state_dict(f)
+        kind = "reference"
+        run = lambda: net.render_rays(rays, bc, fr["aud"], None, fr["latent"], fr["expr"], perturb=1.0)
     ts = []
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            O.render_rays(rays, bc, c, f, fr["aud"], fr["expr"], fr["latent"])
+            run()
             if i >= warmup:
                 ts.append(time.perf_counter() - t0)
     dt = sum(ts) / len(ts)
-    return n_rays / dt, dt, torch.get_num_threads()
+    return n_rays / dt, dt, torch.get_num_threads(), kind
 
 
-def torch_gpu_port_rays_per_s(dev):
-    """The same oracle port in stock PyTorch eager fp32 ON THE GPU (what the reference does after set_default_tensor_type(cuda),
-    audio_exp_nerf.py:598): one 450x450 frame in 25 chunks of 8192 rays (the reference's batchify_rays chunk).  Part of the baseline
-    leg: a reported context number next to the CPU one, never on the product path."""
-    from oracle import render_oracle as O
+def reference_gpu_rays_per_s():
+    """`--impl reference-gpu` (run as a subprocess of the product arm: the reference's import sets process-wide defaults): the UNMODIFIED
+    reference renderer in stock PyTorch eager fp32 on cuda:0, set up the way its own __main__ does (set_default_tensor_type, :598) -- one
+    450x450 frame in 25 chunks of 8192 rays through Network.batchify_rays.  The honest same-box comparison next to the CPU figure."""
+    from oracle import render_oracle as O, ref_import
     fr = O.synthetic_frame(0)
     c, f = O.init_face_nerf(1), O.init_face_nerf(2)
-    to = lambda t: t.to(dev)
-    c, f = {k: to(v) for k, v in c.items()}, {k: to(v) for k, v in f.items()}
-    rays, bc, aud, expr, lat = to(fr["rays"]), to(fr["bc_rgb"]), to(fr["aud"]), to(fr["expr"]), to(fr["latent"])
-    tf32 = torch.backends.cuda.matmul.allow_tf32
+    kind = "reference" if ref_import.available() else "port"
+    dev = torch.device("cuda", 0)
+    if kind == "reference":
+        torch.set_default_tensor_type('torch.cuda.FloatTensor')
+        head = ref_import.import_head(perturb=0.0)
+        net = head.Network(H, W, 1200., O.NEAR, O.FAR, 8192, None, S1, S_IMP)
+        net.face_nerf_coarse.load_state_dict(c)
+        net.face_nerf_fine.load_state_dict(f)
+        net = net.to(dev)
+        to = lambda t: t.to(dev)
+        rays, bc, aud, expr, lat = to(fr["rays"]), to(fr["bc_rgb"]), to(fr["aud"]), to(fr["expr"]), to(fr["latent"])
+        frame = lambda: net.batchify_rays(rays, bc, aud, None, lat, expr, chunk=8192, perturb=0.)
+    else:
+        to = lambda t: t.to(dev)
+        c, f = {k: to(v) for k, v in c.items()}, {k: to(v) for k, v in f.items()}
+        rays, bc, aud, expr, lat = to(fr["rays"]), to(fr["bc_rgb"]), to(fr["aud"]), to(fr["expr"]), to(fr["latent"])
 
-    def frame():
-        for i in range(0, N_RAYS, 8192):
-            O.render_rays(rays[i:i + 8192], bc[i:i + 8192], c, f, aud, expr, lat)
-
-    with torch.device(dev), torch.no_grad():
+        def frame():
+            for i in range(0, N_RAYS, 8192):
+                O.render_rays(rays[i:i + 8192], bc[i:i + 8192], c, f, aud, expr, lat)
+    with torch.no_grad():
         frame()
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -161,24 +189,39 @@ def torch_gpu_port_rays_per_s(dev):
         e1.record()
         torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / 2
-    return {"value": N_RAYS / (ms * 1e-3), "unit": "rays/s", "ms_per_frame": ms, "kind": "port",
-            "sample": f"full 202500-ray frame in 25 chunks of 8192, 1 warm-up + 2 timed frames, torch {torch.__version__} eager fp32 "
-                      f"(allow_tf32={tf32}) on the same GPU"}
+    return {"value": N_RAYS / (ms * 1e-3), "unit": "rays/s", "ms_per_frame": ms, "kind": kind,
+            "sample": f"full 202500-ray frame in 25 chunks of 8192 (batchify_rays), 1 warm-up + 2 timed frames, torch {torch.__version__} eager "
+                      f"fp32 (allow_tf32={torch.backends.cuda.matmul.allow_tf32}) on the same GPU"}
+
+
+def run_sub(extra, timeout=900):
+    """Run another arm of this script in a fresh interpreter and return its JSON line (None on failure)."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__)] + extra, capture_output=True, text=True, timeout=timeout,
+                           env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+        lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+        return json.loads(lines[-1]) if r.returncode == 0 and lines else {"error": (r.stderr or r.stdout)[-300:]}
+    except Exception as e:            # noqa: BLE001 -- a failed baseline leg must not lose the product line
+        return {"error": repr(e)[:300]}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = 2048
-    v, dt, cores = cpu_reference_rays_per_s(n, args.steps, max(1, args.warmup))
+    if args.impl == "reference-gpu":
+        emit(dict(reference_gpu_rays_per_s(), impl="reference-gpu"))
+        return
+    n = args.ref_rays
+    v, dt, cores, kind = cpu_reference_rays_per_s(n, args.steps, max(1, args.warmup))
+    what = "the reference's own Network.render_rays (oracle/_ref)" if kind == "reference" else "oracle port of the reference algorithm"
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "HeadNeRF 450x450 frame render (coarse 64 + fine 192 samples), reference algorithm on host CPU",
-                       "sample": f"{n} rays of the frame per step"},
-            "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
-                             "sample": f"{n} of 202500 frame rays per step, torch {torch.__version__} fp32, "
+            "config": {"workload": f"HeadNeRF 450x450 frame render (coarse 64 + fine 192 samples), {what} on the host CPU",
+                       "sample": f"{n} rays of the frame per step", "perturb": 1.0, "mlp_mode": "fp32 (torch CPU)"},
+            "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": kind,
+                             "sample": f"{n} of 202500 frame rays per step ({dt:.2f} s), perturb=1, torch {torch.__version__} fp32, "
                                        f"{torch.backends.cpu.get_cpu_capability()}"},
             "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -305,6 +348,59 @@ def train_step_bench(M, dev, steps, mode="bf16", rank=0, world=1):
     return out
 
 
+def sampling_standalone(M, dev, n_rays, reps=20):
+    """The two sampling kernels alone on frame-sized resident tensors (perturb > 0 forms: stratified depths + importance sampling with
+    in-kernel draws), `reps` back-to-back launches per event pair.  Algorithmic bytes per ray (SURVEY.md 8d): coarse 44 in + 256 out;
+    sample_pdf + merge 512 in (z, weights) + 768 (merged z) + 4 (z_std) out -- the draws and z_samples never touch HBM."""
+    from ideal_nerf_b200 import ops, synthetic as S
+    cam = S.camera()
+    rays = ops.get_rays_packed(H, W, cam["focal"], cam["c2w"].to(dev), S.NEAR, S.FAR)[:n_rays].contiguous()
+    g = torch.Generator(device=dev).manual_seed(12)
+    w = torch.rand(n_rays, S1, device=dev, generator=g) ** 4
+    st = ops.rng_state(dev)
+    z = ops.sample_coarse_rng(rays, S1, st, advance=False)
+    out = {}
+    for name, fn, nbytes in (("inerf_sample_coarse_rng", lambda: ops.sample_coarse_rng(rays, S1, st, advance=False), 44 + 4 * S1),
+                             ("inerf_importance_sample_rng", lambda: ops.importance_sample_rng(z, w, S_IMP, st, advance=False),
+                              8 * S1 + 4 * (S1 + S_IMP) + 4)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out[name] = {"ms": ms, "bytes": n_rays * nbytes, "gbs": n_rays * nbytes / (ms * 1e-3) / 1e9}
+    return out
+
+
+def build_torso_network(mode, dev):
+    """BASELINE.json config 4: head + torso renderer (train_torso.py:186), random init + density preset on all four FaceNeRFs."""
+    import ideal_nerf_b200 as M
+    from ideal_nerf_b200 import synthetic as S, ops
+    cam, fr = S.camera(), S.frame_inputs(0)
+    a = M.default_args(dim_aud=64, dim_expr=79, perturb=1.0, mlp_mode=mode, N_samples=S1, N_importance=S_IMP, near=S.NEAR, far=S.FAR)
+    net = M.TorsoNetwork(H, W, cam["focal"], S.NEAR, S.FAR, 1 << 20, S1, S_IMP, args=a, dim_expr=79)
+    torch.manual_seed(77)
+    net.apply(M.init_weights)
+    net = net.to(dev).eval()
+    g = torch.Generator().manual_seed(3)
+    expr = torch.randn(79, generator=g).to(dev)
+    aud, lat, pose = fr["aud"].to(dev), fr["latent"].to(dev), fr["pose"].to(dev)
+    rays = ops.get_rays_packed(H, W, cam["focal"], cam["c2w"].to(dev), S.NEAR, S.FAR)
+    sub = rays[::197].contiguous()
+    with torch.no_grad():
+        sig = net.torso_signal(aud, pose)
+        for fn in (net.face_nerf_coarse, net.face_nerf_fine):
+            S.normalise_density_(fn, sub, aud, expr, lat)
+        for fn in (net.torso_coarse_nerf, net.torso_fine_nerf):
+            S.normalise_density_(fn, sub, sig, None, None)
+    return net, rays, fr["bc_rgb"].to(dev), aud, pose, expr, lat
+
+
 def run_ours(args):
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -319,8 +415,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     M, net, fr, cam = build_network(args.mode, dev)
-    from ideal_nerf_b200 import ops
-    from ideal_nerf_b200.frame import FrameRenderer, band
+    from ideal_nerf_b200 import ops, synthetic as S
+    from ideal_nerf_b200.frame import FrameRenderer, band, render_video
     M._lib.check(M.lib().inerf_device_check(), "inerf_device_check")
     fr_r = FrameRenderer(net, rank, world)
 
@@ -333,11 +429,10 @@ def run_ours(args):
 
     @torch.no_grad()
     def step_resident():
-        out = None
-        for _ in range(frames):
-            ret, _ = fr_r.render_band(res["pose"], res["aud"], res["expr"], res["latent"], res["bc"], perturb=1.0)
-            out = fr_r.gather_image(ret["rgb_map"], N_RAYS)
-        return out
+        """`frames` frames, each ray-sharded over the ranks; the band all-gather of frame i overlaps the kernels of frame i+1."""
+        hs = [fr_r.render_frame(res["pose"], res["aud"], res["expr"], res["latent"], res["bc"], perturb=1.0, async_op=True)
+              for _ in range(frames)]
+        return [h.wait() for h in hs][-1]
 
     out_h = torch.empty((N_RAYS, 3)).pin_memory()
     h2d = sum(host[k].numel() * 4 for k in host)
@@ -381,10 +476,12 @@ def run_ours(args):
     if sampler:
         sampler.start()
     ops.LAUNCHES["count"] = 0
-    with ops.kernel_timing() as kt:
-        total_ms = timed(step_resident, args.steps)
+    total_ms = timed(step_resident, args.steps)          # the headline: no per-kernel events inside this region
     launches = ops.LAUNCHES["count"]
     clocks = sampler.stop() if sampler else None
+    # second, identical pass with a CUDA-event pair around every launch (on the launching stream) for the roofline / breakdown
+    with ops.kernel_timing() as kt:
+        timed_ms_events = timed(step_resident, args.steps)
     ksum = kt.summary()
 
     for _ in range(2):
@@ -395,28 +492,69 @@ def run_ours(args):
     value = rays_per_step * args.steps / (total_ms * 1e-3)
     e2e_value = rays_per_step * args.steps / (t_e2e * 1e-3)
 
+    # ---- config 5: eval video, per-frame audio / expression codes, rays of EVERY frame sharded over the ranks -----------------------
+    video = None
+    if args.video_frames > 0:
+        nf = args.video_frames
+        aud_v, expr_v = S.video_codes(nf, 0)
+        aud_v, expr_v = aud_v.to(dev), expr_v.to(dev)
+        seq = [(res["pose"], aud_v[i], expr_v[i]) for i in range(nf)]
+        with torch.no_grad():
+            render_video(fr_r, seq[:4], res["latent"], res["bc"], perturb=0.)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            vid = render_video(fr_r, seq, res["latent"], res["bc"], perturb=0.)          # eval: perturb = 0 (eval_aud_exp_nerf.py)
+            e1.record()
+            barrier()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            v_ms = float(ms.item())
+            # latency of ONE frame: inputs resident, render -> gather -> to8b -> pinned host copy, a synchronise per frame
+            lat_ms = []
+            one = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+            for i in range(12):
+                barrier()
+                t0 = time.perf_counter()
+                pose_i, aud_i, expr_i = seq[i]
+                rgb = fr_r.render_frame(pose_i, aud_i, expr_i, res["latent"], res["bc"], 0.)
+                if rank == 0:
+                    one.copy_(ops.to8b(rgb).reshape(H, W, 3), non_blocking=True)
+                torch.cuda.synchronize()
+                lat_ms.append((time.perf_counter() - t0) * 1e3)
+            lat = torch.tensor(sorted(lat_ms[2:])[len(lat_ms[2:]) // 2], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(lat, op=dist.ReduceOp.MAX)
+        video = {"frames": nf, "ms_total": v_ms, "fps": nf / (v_ms * 1e-3), "rays_per_s": nf * N_RAYS / (v_ms * 1e-3),
+                 "ms_per_frame": v_ms / nf, "latency_ms_per_frame": float(lat.item()), "perturb": 0.0,
+                 "codes": "seeded Gaussian random walk of aud (64) / expr (76), sigma 0.1 per frame; pose fixed",
+                 "sharding": f"rays of every frame block-partitioned over {world} GPU(s), one all-gather per frame overlapped with the next frame",
+                 "output": "uint8 frames in one pinned host array (to8b on device)",
+                 "checksum": int(vid.to(torch.int64).sum()) if rank == 0 else None}
+
     train_bf16 = None if args.no_train else train_step_bench(M, dev, 5, "bf16", rank, world)      # every rank takes part (gradient all-reduce)
 
     if rank == 0:
         pk, pk_kind = peaks()
         n_mlp, mlp_ms = ksum.get("inerf_mlp_fwd", (0, 0.0))
-        # dominant kernel: FaceNeRF forward.  Algorithmic FLOPs of the launches in the timed region / their event time.
+        # dominant kernel: FaceNeRF forward.  Algorithmic FLOPs of the launches in the (second) timed region / their event time.
         pts_per_step_rank = (hi - lo) * (S1 + S1 + S_IMP) * frames
         mlp_flops = pts_per_step_rank * args.steps * FLOP_PER_POINT_FWD
         achieved = mlp_flops / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else None
         peak = pk["bf16_tflops_sustained"]
-        n_cmp, cmp_ms = ksum.get("inerf_composite_fwd", (0, 0.0))
-        cmp_bytes = (hi - lo) * frames * args.steps * ((24 * S1 + 48) + (24 * (S1 + S_IMP) + 48))
         with torch.no_grad():
             sa_bytes, sa_ms = composite_standalone(M, dev, N_RAYS)      # always frame-sized: inputs larger than L2
+            samp = sampling_standalone(M, dev, N_RAYS)
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.mode == "fp32" else "bf16", "data": "synthetic",
             "config": {"workload": "HeadNeRF full 450x450 frame render (coarse 64 + fine 192 samples), FaceNeRF dim_aud=64 dim_expr=76",
                        "frames_per_step": frames, "rays_per_rank_per_step": (hi - lo) * frames, "mlp_mode": args.mode,
-                       "perturb": 1.0, "l2": "inputs larger than L2 (raw 207+622 MB per frame pass)",
-                       "parallelism": f"rays block-partitioned over {world} GPU(s), NCCL gather of bands"},
+                       "perturb": 1.0, "rng": "in-kernel Philox4x32-10 (stratified jitter + importance draws)",
+                       "l2": "inputs larger than L2 (raw 207+622 MB per frame pass)",
+                       "parallelism": f"rays block-partitioned over {world} GPU(s), one NCCL all-gather of the bands per frame"},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d * frames,
                     "d2h_bytes_per_step": N_RAYS * 3 * 4 * frames, "ms_per_step": t_e2e / args.steps},
             "gpu_launches": launches,
@@ -424,28 +562,88 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "kernel": "inerf_mlp_fwd", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": mlp_traffic(),
                          "peak_kind": f"bf16 dense sustained, {pk_kind}", "launches": n_mlp, "kernel_ms_total": mlp_ms,
-                         "share_of_step": mlp_ms / total_ms if total_ms else None},
+                         "share_of_step": mlp_ms / timed_ms_events if timed_ms_events else None,
+                         "how": "second pass of the same steps with a CUDA-event pair around every launch; `value` is the event-free pass"},
             "roofline_composite": {"bound": "hbm", "kernel": "inerf_composite_fwd",
                                    "achieved": sa_bytes / (sa_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                    "frac": sa_bytes / (sa_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
-                                   "how": "stand-alone, 20 back-to-back launches per event pair on frame-sized resident inputs (S=64 and S=192)",
-                                   "in_step": {"achieved": cmp_bytes / (cmp_ms * 1e-3) / 1e9 if cmp_ms > 0 else None, "launches": n_cmp,
-                                               "kernel_ms_total": cmp_ms, "note": "one event pair per 0.1 ms launch: includes event overhead"}},
+                                   "how": "stand-alone, 20 back-to-back launches per event pair on frame-sized resident inputs (S=64 and S=192)"},
+            "roofline_sampling": {"bound": "hbm", "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                  "kernels": {k: {"achieved": v["gbs"], "frac": v["gbs"] / pk["hbm_gbs"], "ms": v["ms"], "bytes": v["bytes"]}
+                                              for k, v in samp.items()},
+                                  "how": "stand-alone on 202 500 rays, 20 back-to-back launches per event pair"},
             "kernels_ms": {k: round(v[1], 3) for k, v in ksum.items()},
         }
+        if video is not None:
+            line["config5_video"] = video
         if train_bf16 is not None:
             line["train_step"] = train_bf16
+        if world == 1 and not args.no_extra:
+            line.update(extra_single_gpu(M, net, dev, res, args))
         if world == 1 and not args.no_train:
             line["train_step_fp32"] = train_step_bench(M, dev, 3, "fp32")
         if world == 1 and not args.no_cpu_baseline:
-            v, dt, cores = cpu_reference_rays_per_s(3072, 2, 1)
-            line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
-                                    "sample": f"3072 of 202500 frame rays, 1 warm-up + 2 timed runs ({dt:.2f} s each), "
-                                              f"torch {torch.__version__} fp32 {torch.backends.cpu.get_cpu_capability()}"}
-            line["torch_gpu_baseline"] = torch_gpu_port_rays_per_s(dev)
+            ref = run_sub(["--impl", "reference", "--steps", "2", "--warmup", "1", "--ref-rays", "3072"])
+            if ref and "cpu_baseline" in ref:
+                line["cpu_baseline"] = ref["cpu_baseline"]
+            else:                                              # the subprocess failed: time the port in-process instead
+                v, dt, cores, kind = cpu_reference_rays_per_s(3072, 2, 1)
+                line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": kind, "sample": f"3072 of 202500 frame rays ({dt:.2f} s per run)",
+                                        "note": str(ref)[:200]}
+            line["torch_gpu_baseline"] = run_sub(["--impl", "reference-gpu"])
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def extra_single_gpu(M, net, dev, res, args):
+    """Extra keys measured on one GPU: the fp32-gate mode's frame rate, bf16-vs-fp32 render parity on the benchmark frame, and
+    BASELINE.json config 4 (head + torso composited frame)."""
+    from ideal_nerf_b200 import ops
+    out = {}
+
+    def time_frames(fn, n):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    with torch.no_grad():
+        rays = ops.get_rays_packed(H, W, net.focal, res["pose"][:3, :4], net.near, net.far)
+        render = lambda p: net.render_rays(rays, res["bc"], res["aud"], None, res["latent"], res["expr"], perturb=p)
+        # parity of the benchmark mode on the benchmark frame (perturb = 0 so both modes see the same depths): bf16 vs the fp32 kernels
+        mode0 = args.mode
+        r_fast = render(0.)
+        net.set_mlp_mode("fp32")
+        r32 = render(0.)
+        ms32 = time_frames(lambda: render(1.0), 1)
+        net.set_mlp_mode(mode0)
+        mse = float(torch.mean((r_fast["rgb_map"] - r32["rgb_map"]) ** 2))
+        out["parity"] = {"against": "this repo's fp32 (FFMA) kernels on the same 202 500-ray frame, perturb=0 (the fp32 kernels are checked "
+                                    "against the reference's outputs at <= 1e-3 in tests/test_gpu_parity.py)",
+                         "psnr_db": float(-10. * torch.log10(torch.tensor(mse))) if mse > 0 else None,
+                         "max_abs": float((r_fast["rgb_map"] - r32["rgb_map"]).abs().max()),
+                         "acc_max_abs": float((r_fast["acc_map"] - r32["acc_map"]).abs().max())}
+        out["render_fp32"] = {"rays_per_s": N_RAYS / (ms32 * 1e-3), "ms_per_frame": ms32, "mlp_mode": "fp32 (FFMA, the <= 1e-3 max-abs mode)",
+                              "frames": 1}
+        # config 4: head + torso composited frame with background blending (test_torso.py:516-523)
+        tn, trays, bc, aud, pose, expr, lat = build_torso_network(args.mode, dev)
+        step = lambda: tn(trays, trays, bc, aud, pose, expr, lat, perturb=1.0)
+        for _ in range(2):
+            step()
+        ops.LAUNCHES["count"] = 0
+        ms4 = time_frames(step, max(3, args.steps // 2))
+        out["config4_head_torso"] = {"rays_per_s": N_RAYS / (ms4 * 1e-3), "ms_per_frame": ms4, "mlp_mode": args.mode,
+                                     "point_evals_per_ray": 2 * (S1 + S1 + S_IMP),
+                                     "workload": "HeadNeRF + TorsoNeRF 450x450 frame: two coarse+fine FaceNeRF pairs (torso cond 106 = aud 64 + "
+                                                 "gamma_3(euler) 21 + gamma_3(trans) 21), rgb = rgb_head * last_weight_torso + rgb_fg_torso",
+                                     "perturb": 1.0}
+    return out
 
 
 _RESULT_OUT = None
@@ -469,12 +667,15 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference", "reference-gpu"])
+    ap.add_argument("--ref-rays", dest="ref_rays", type=int, default=2048, help="rays per step of the reference arm (bounded sample)")
+    ap.add_argument("--video-frames", dest="video_frames", type=int, default=200)
     ap.add_argument("--mode", type=str, default=os.environ.get("INERF_BENCH_MODE", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     ap.add_argument("--no-train", dest="no_train", action="store_true")
+    ap.add_argument("--no-extra", dest="no_extra", action="store_true", help="skip the fp32-mode render, parity and config-4 keys")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.impl in ("reference", "reference-gpu"):
         run_reference(args)
     else:
         run_ours(args)

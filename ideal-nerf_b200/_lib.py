@@ -14,7 +14,7 @@ REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 SO_PATH = os.environ.get("INERF_SO") or os.path.join(PKG_DIR, "libinerf_b200.so")     # INERF_SO: profiling builds only
 SOURCES = ["api.cu", "rays.cu", "composite.cu", "sample_pdf.cu", "mlp_fp32.cu", "mlp_fp32_bwd.cu", "mlp_bf16.cu", "mlp_bf16_bwd.cu",
-           "mlp_bf16_dw.cu", "mlp_bf16_v2.cu", "audio_net.cu"]
+           "mlp_bf16_dw.cu", "audio_net.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--shared"]
 
@@ -45,6 +45,11 @@ SIGNATURES = {
     "inerf_device_check": (_I, []),
     "inerf_get_rays": (_I, [_I, _I, _F, _F, _F, _P, _I, _F, _F, _P, _P]),
     "inerf_get_rays_at": (_I, [_P, _I, _F, _F, _F, _P, _I, _F, _F, _P, _P]),
+    "inerf_get_rays_range": (_I, [_I, _I, _F, _F, _F, _P, _I, _F, _F, _I, _I, _P, _P]),
+    "inerf_rng_advance": (_I, [_P, ctypes.c_uint64, _P]),
+    "inerf_sample_coarse_rng": (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P]),
+    "inerf_flag_nonfinite": (_I, [_PARAMS, ctypes.POINTER(ctypes.c_int64), _I, _P, _P]),
+    "inerf_importance_sample_rng": (_I, [_P, _P, _I, _I, _I, _P, ctypes.c_uint32, _P, _P, _P, _P]),
     "inerf_pack_rays": (_I, [_P, _P, _I, _F, _F, _P, _P]),
     "inerf_posenc": (_I, [_P, _L, _I, _I, _P, _P]),
     "inerf_to8b": (_I, [_P, _L, _P, _P]),
@@ -85,19 +90,41 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-    """Compile csrc/*.cu for sm_100a into ideal-nerf_b200/libinerf_b200.so (nvcc cross-compiles without a GPU)."""
+    """Compile csrc/*.cu for sm_100a into ideal-nerf_b200/libinerf_b200.so (nvcc cross-compiles without a GPU).  One object per source,
+    compiled in parallel and cached under build/obj by (source, header) modification time, then one device link."""
     if not force and not _stale():
         return SO_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libinerf_b200.so")
-    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("INERF_EXTRA_NVCC", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH + ".tmp"] + SOURCES
-    r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    extra = os.environ.get("INERF_EXTRA_NVCC", "").split()
+    objdir = os.path.join(REPO_ROOT, "build", "obj" + ("_" + str(abs(hash(tuple(extra))) % 10 ** 8) if extra else ""))
+    os.makedirs(objdir, exist_ok=True)
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + [os.path.join(REPO_ROOT, "include", "inerf_b200.h")]
+    t_hdr = max(os.path.getmtime(h) for h in hdrs)
+    flags = [f for f in NVCC_FLAGS if f != "--shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src[:-3] + ".o")
+        spath = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(t_hdr, os.path.getmtime(spath)):
+            return obj, ""
+        r = subprocess.run([nvcc] + flags + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, spath],
+                           cwd=CSRC, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + r.stdout + r.stderr)
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        res = list(ex.map(compile_one, SOURCES))
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-Xcompiler", "-fPIC", "-o", SO_PATH + ".tmp"] + [o for o, _ in res],
+                       capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
     os.replace(SO_PATH + ".tmp", SO_PATH)
     if verbose:
-        print(r.stderr)
+        print("".join(e for _, e in res))
     return SO_PATH
 
 

@@ -848,7 +848,6 @@ int mlp_bf16_launch(const MlpArgs& a, bool embedded, cudaStream_t st) {
         if (abl >= 1 && abl <= 24) return check_launch("inerf_mlp_fwd[bf16,ablation]");
     }
 #endif
-    if (!a.save_img && getenv("INERF_MLP_V2")) return mlp_bf16_v2_launch(a, st);      // a.trace: v2 writes phase timings there
     if (a.save_img) {
         if (!a.save_mask) return fail(INERF_E_ARG, "mlp_bf16: save_mask is NULL");
         static thread_local int save_dev = -1;

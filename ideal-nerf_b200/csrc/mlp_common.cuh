@@ -45,7 +45,6 @@ int mlp_fp32_bwd_launch(const InerfNetDims* dims, const float* const* params_hos
 size_t mlp_fp32_bwd_args_bytes();
 int mlp_bf16_hang_info(int32_t* out8);
 void mlp_bf16_stage_offsets(uint32_t (*off)[2][5]);      // [11 layers][half][K-block index in issue order] -> byte offset in the packed blob
-int mlp_bf16_v2_launch(const MlpArgs& a, cudaStream_t st);   // cta_group::2 inference kernel (mlp_bf16_v2.cu), same blob / bias tiles
 // bf16 training path (mlp_bf16_bwd.cu, mlp_bf16_dw.cu, mlp_fp32_bwd.cu)
 int mlp_bf16_bwd_packed_bytes(const InerfNetDims* d, size_t* bytes);
 int mlp_bf16_bwd_pack(const InerfNetDims* d, const float* const* params_host, void* packed, cudaStream_t st);

@@ -4,6 +4,7 @@
 // intrinsics (__fmul_rn/__fadd_rn are never contracted into FMA), so the depths equal the
 // reference's tensor-op-at-a-time fp32 values.
 #include "common.cuh"
+#include "philox.cuh"
 
 using namespace inerf;
 
@@ -20,11 +21,12 @@ __device__ __forceinline__ void store_ray(float* __restrict__ r, float ox, float
     r[8] = __fdiv_rn(dx, nrm); r[9] = __fdiv_rn(dy, nrm); r[10] = __fdiv_rn(dz, nrm);
 }
 
-__global__ void get_rays_kernel(int H, int W, float focal, float cx, float cy, const float* __restrict__ c2w,
+// rays of the pixels [first, first + count) of the row-major H x W grid; rays[0] is pixel `first`
+__global__ void get_rays_kernel(int W, int first, int count, float focal, float cx, float cy, const float* __restrict__ c2w,
                                 int rs, float near_, float far_, float* __restrict__ rays) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= H * W) return;
-    int row = idx / W, col = idx - row * W;
+    if (idx >= count) return;
+    int row = (first + idx) / W, col = (first + idx) - row * W;
     // camera-frame direction ((i-cx)/f, -(j-cy)/f, -1)
     float c0 = __fdiv_rn(__fsub_rn((float)col, cx), focal);
     float c1 = -__fdiv_rn(__fsub_rn((float)row, cy), focal);
@@ -86,9 +88,18 @@ extern "C" int inerf_get_rays(int H, int W, float focal, float cx, float cy, con
     if (H <= 0 || W <= 0 || (int64_t)H * W > (1 << 30) || c2w_row_stride < 4)
         return fail(INERF_E_SHAPE, "inerf_get_rays: bad H/W/c2w_row_stride");
     int n = H * W;
-    get_rays_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(H, W, focal, cx, cy, c2w, c2w_row_stride, near_,
-                                                                    far_, rays);
+    get_rays_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(W, 0, n, focal, cx, cy, c2w, c2w_row_stride, near_, far_, rays);
     return check_launch("inerf_get_rays");
+}
+
+extern "C" int inerf_get_rays_range(int H, int W, float focal, float cx, float cy, const float* c2w, int c2w_row_stride,
+                                    float near_, float far_, int first, int count, float* rays, void* stream) {
+    if (H <= 0 || W <= 0 || (int64_t)H * W > (1 << 30) || c2w_row_stride < 4) return fail(INERF_E_SHAPE, "inerf_get_rays_range: bad H/W/c2w_row_stride");
+    if (first < 0 || count < 0 || (int64_t)first + count > (int64_t)H * W) return fail(INERF_E_SHAPE, "inerf_get_rays_range: [first, first+count) outside the frame");
+    if (count == 0) return INERF_OK;
+    if (!c2w || !rays) return fail(INERF_E_ARG, "inerf_get_rays_range: NULL pointer");
+    get_rays_kernel<<<(count + 255) / 256, 256, 0, as_stream(stream)>>>(W, first, count, focal, cx, cy, c2w, c2w_row_stride, near_, far_, rays);
+    return check_launch("inerf_get_rays_range");
 }
 
 extern "C" int inerf_pack_rays(const float* rays_o, const float* rays_d, int n, float near_, float far_, float* rays,
@@ -144,21 +155,30 @@ __device__ __forceinline__ float coarse_z(float near_, float far_, float t, int 
     return __fdiv_rn(1.0f, __fadd_rn(a, b));
 }
 
+template <bool RNG>
 __global__ void sample_coarse_kernel(const float* __restrict__ rays, int n, int ray_stride, int s,
-                                     const float* __restrict__ t_vals, const float* __restrict__ t_rand, int lindisp,
-                                     float* __restrict__ z) {
+                                     const float* __restrict__ t_vals, const float* __restrict__ t_rand,
+                                     const unsigned long long* __restrict__ rng_state, int lindisp, float* __restrict__ z) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)n * s) return;
     int ray = (int)(idx / s);
     int i = (int)(idx - (int64_t)ray * s);
     float near_ = rays[(size_t)ray * ray_stride + 6], far_ = rays[(size_t)ray * ray_stride + 7];
     float zi = coarse_z(near_, far_, t_vals[i], lindisp);
-    if (t_rand) {
+    if (RNG || t_rand) {
         // mids = .5*(z[1:]+z[:-1]); upper = [mids, z[-1]]; lower = [z[0], mids]; z = lower + (upper-lower)*r
         float lo = zi, hi = zi;
         if (i > 0) lo = __fmul_rn(0.5f, __fadd_rn(zi, coarse_z(near_, far_, t_vals[i - 1], lindisp)));
         if (i < s - 1) hi = __fmul_rn(0.5f, __fadd_rn(coarse_z(near_, far_, t_vals[i + 1], lindisp), zi));
-        float r = (i == s - 1) ? 1.0f : t_rand[idx];       // t_rand[..., -1] = 1.0  (:326)
+        float r;
+        if constexpr (RNG) {                                // draw idx of the stream: word idx & 3 of Philox block idx >> 2
+            const Philox4 q = philox_at(rng_state, (uint64_t)idx >> 2, INERF_RNG_STREAM_COARSE);
+            const uint32_t w = (idx & 2) ? ((idx & 1) ? q.w : q.z) : ((idx & 1) ? q.y : q.x);
+            r = u01(w);
+        } else {
+            r = t_rand[idx];
+        }
+        if (i == s - 1) r = 1.0f;                           // t_rand[..., -1] = 1.0  (:326)
         zi = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), r));
     }
     z[idx] = zi;
@@ -170,9 +190,61 @@ extern "C" int inerf_sample_coarse(const float* rays, int n, int ray_stride, int
     if (n == 0) return INERF_OK;
     if (!rays || !t_vals || !z) return fail(INERF_E_ARG, "inerf_sample_coarse: NULL pointer");
     int64_t total = (int64_t)n * s;
-    sample_coarse_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(rays, n, ray_stride, s, t_vals,
-                                                                                        t_rand, lindisp, z);
+    sample_coarse_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(rays, n, ray_stride, s, t_vals, t_rand,
+                                                                                               nullptr, lindisp, z);
     return check_launch("inerf_sample_coarse");
+}
+
+extern "C" int inerf_sample_coarse_rng(const float* rays, int n, int ray_stride, int s, const float* t_vals, const uint64_t* rng_state,
+                                       int lindisp, float* z, void* stream) {
+    if (n < 0 || s <= 0 || s > 4096 || ray_stride < 8) return fail(INERF_E_SHAPE, "inerf_sample_coarse_rng: bad n/s/stride");
+    if (n == 0) return INERF_OK;
+    if (!rays || !t_vals || !z || !rng_state) return fail(INERF_E_ARG, "inerf_sample_coarse_rng: NULL pointer");
+    int64_t total = (int64_t)n * s;
+    sample_coarse_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(
+        rays, n, ray_stride, s, t_vals, nullptr, reinterpret_cast<const unsigned long long*>(rng_state), lindisp, z);
+    return check_launch("inerf_sample_coarse_rng");
+}
+
+// ---------------------------------------------------------------------------------------------
+// RNG state upkeep and the NaN / Inf scan of render_rays' outputs (audio_exp_nerf.py:367-369)
+// ---------------------------------------------------------------------------------------------
+__global__ void rng_advance_kernel(unsigned long long* state, unsigned long long inc) { state[1] += inc; }
+
+extern "C" int inerf_rng_advance(uint64_t* rng_state, uint64_t increment, void* stream) {
+    if (!rng_state) return fail(INERF_E_ARG, "inerf_rng_advance: NULL pointer");
+    rng_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<unsigned long long*>(rng_state), (unsigned long long)increment);
+    return check_launch("inerf_rng_advance");
+}
+
+struct ScanArgs { const float* x[INERF_MAX_SCAN]; long long n[INERF_MAX_SCAN]; int k; };
+
+__global__ void flag_nonfinite_kernel(ScanArgs a, int* __restrict__ flags) {
+    const float* x = a.x[blockIdx.y];
+    const long long n = a.n[blockIdx.y];
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        bad |= !isfinite(x[i]);
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags, 1 << blockIdx.y);
+}
+
+extern "C" int inerf_flag_nonfinite(const float* const* xs_host, const int64_t* ns_host, int k, int32_t* flags, void* stream) {
+    if (k < 0 || k > INERF_MAX_SCAN) return fail(INERF_E_SHAPE, "inerf_flag_nonfinite: 0 <= k <= INERF_MAX_SCAN tensors");
+    if (k == 0) return INERF_OK;
+    if (!xs_host || !ns_host || !flags) return fail(INERF_E_ARG, "inerf_flag_nonfinite: NULL pointer");
+    ScanArgs a{};
+    long long nmax = 0;
+    for (int i = 0; i < k; ++i) {
+        if (ns_host[i] < 0 || (ns_host[i] > 0 && !xs_host[i])) return fail(INERF_E_ARG, "inerf_flag_nonfinite: NULL tensor / negative size");
+        a.x[i] = xs_host[i]; a.n[i] = ns_host[i];
+        nmax = ns_host[i] > nmax ? ns_host[i] : nmax;
+    }
+    a.k = k;
+    if (nmax == 0) return INERF_OK;
+    long long blocks = (nmax + 1023) / 1024;
+    if (blocks > 592) blocks = 592;
+    flag_nonfinite_kernel<<<dim3((unsigned)blocks, k), 256, 0, as_stream(stream)>>>(a, flags);
+    return check_launch("inerf_flag_nonfinite");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -24,6 +24,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "philox.cuh"
 
 using namespace inerf;
 
@@ -189,6 +190,140 @@ __global__ void __launch_bounds__(256) sample_pdf_kernel(PdfArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Stochastic branch (perturb > 0, helper.py:282-283: u = torch.rand(N, n_imp)) with the draws made IN the kernel.
+//
+// Parity for this branch is defined on supplied draws (the kernel above); with the reference's own generator out of reach the
+// only requirements are u ~ iid U[0,1) per ray and the outputs the renderer consumes: sort(cat(z, z_samples)) and std(z_samples),
+// both symmetric in the order of the draws.  So the kernel draws the ORDER STATISTICS of n_imp uniforms directly --
+// U_(k) = (E_1 + ... + E_k) / (E_1 + ... + E_{n_imp+1}) with E_i iid Exp(1) (Renyi's representation) -- one warp scan instead of a
+// 128-key bitonic sort, no (N, n_imp) tensor of draws in HBM (512 B/ray written by torch.rand and read back), and a plain fp32
+// warp-shuffle CDF (policy INERF_PDF_FAST: bit-exactness against the CPU is moot when u is random).  z_samples come out ascending.
+// ---------------------------------------------------------------------------------------------
+struct PdfRngArgs {
+    const float* z_coarse; const float* w_coarse; int n, s1, n_imp;
+    const unsigned long long* rng_state; unsigned stream_id;
+    float* z_samples;            // may be NULL
+    float* z_merged; float* z_std;
+    int warp_floats, runs;       // runs = Philox blocks per lane = ceil(ceil(n_imp / 32) / 4)
+};
+
+__global__ void __launch_bounds__(256) importance_rng_kernel(PdfRngArgs a) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int ray = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (ray >= a.n) return;
+    const int s1 = a.s1, nb = s1 - 1, nw = s1 - 2, n_imp = a.n_imp, tot = s1 + n_imp;
+    float* zc = smem + (size_t)wib * a.warp_floats;      // [s1]   coarse depths
+    float* bsm = zc + ((s1 + 3) & ~3);                   // [nb]   bin mid-points
+    float* csm = bsm + ((nb + 3) & ~3);                  // [nb]   cdf
+    float* zsm = csm + ((nb + 3) & ~3);                  // [n_imp] uniforms, then samples
+    float* osm = zsm + ((n_imp + 3) & ~3);               // [tot]  merged row
+
+    const float* zrow = a.z_coarse + (size_t)ray * s1;
+    const float* wrow = a.w_coarse + (size_t)ray * s1 + 1;       // weights[..., 1:-1]
+    for (int j = lane; j < s1; j += 32) zc[j] = zrow[j];
+    __syncwarp();
+    for (int j = lane; j < nb; j += 32) bsm[j] = 0.5f * (zc[j + 1] + zc[j]);
+
+    // cdf: lane owns the contiguous run [lane*E, lane*E+E) of the nw weights
+    const int E = (nw + 31) >> 5;
+    const int j0 = min(nw, lane * E), j1 = min(nw, j0 + E);
+    float local = 0.f;
+    for (int j = j0; j < j1; ++j) local += wrow[j] + 1e-5f;
+    float incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const float inv_S = 1.0f / __shfl_sync(0xffffffffu, incl, 31);
+    float run = incl - local;
+    for (int j = j0; j < j1; ++j) {
+        run += wrow[j] + 1e-5f;
+        csm[j + 1] = run * inv_S;
+    }
+    if (lane == 0) csm[0] = 0.0f;
+
+    // sorted uniforms: lane owns draws [k0, k1), k0 = lane * R
+    const int R = (n_imp + 31) >> 5;
+    const int k0 = min(n_imp, lane * R), k1 = min(n_imp, k0 + R);
+    const uint64_t base = (uint64_t)ray * (uint64_t)(32 * a.runs + 1);
+    float acc = 0.f;
+    for (int b = 0; b < a.runs; ++b) {
+        const Philox4 q = philox_at(a.rng_state, base + (uint64_t)(lane * a.runs + b), a.stream_id);
+        const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int k = k0 + 4 * b + t;
+            if (k < k1) { acc += -__logf(u01_open0(w4[t])); zsm[k] = acc; }
+        }
+    }
+    float eincl = acc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, eincl, o);
+        if (lane >= o) eincl += t;
+    }
+    const float e_tail = -__logf(u01_open0(philox_at(a.rng_state, base + (uint64_t)(32 * a.runs), a.stream_id).x));
+    const float inv_T = 1.0f / (__shfl_sync(0xffffffffu, eincl, 31) + e_tail);
+    const float e_off = eincl - acc;
+    __syncwarp();
+
+    // invert the CDF (searchsorted right=True) for the lane's own draws
+    float sum = 0.f;
+    for (int k = k0; k < k1; ++k) {
+        const float u = fminf((zsm[k] + e_off) * inv_T, 1.0f);
+        int lo = 0, hi = nb;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (csm[mid] <= u) lo = mid + 1; else hi = mid;
+        }
+        const int below = max(lo - 1, 0), above = min(lo, nb - 1);
+        const float cb = csm[below], ca = csm[above];
+        float den = ca - cb;
+        if (den < 1e-5f) den = 1.0f;
+        const float t = (u - cb) / den;
+        const float bb = bsm[below], ba = bsm[above];
+        const float zs = bb + t * (ba - bb);
+        zsm[k] = zs;
+        sum += zs;
+    }
+    __syncwarp();
+    if (a.z_std) {
+        const float mean = warp_sum(sum) / (float)n_imp;
+        float sq = 0.f;
+        for (int k = k0; k < k1; ++k) { const float d = zsm[k] - mean; sq += d * d; }
+        sq = warp_sum(sq);
+        if (lane == 0) a.z_std[ray] = sqrtf(sq / (float)n_imp);
+    }
+    if (a.z_samples) {
+        float* zo = a.z_samples + (size_t)ray * n_imp;
+        for (int k = lane; k < n_imp; k += 32) zo[k] = zsm[k];
+    }
+    // rank merge of the two ascending lists (ties: coarse depths first)
+    for (int j = lane; j < s1; j += 32) {
+        const float v = zc[j];
+        int lo = 0, hi = n_imp;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (zsm[mid] < v) lo = mid + 1; else hi = mid; }
+        osm[j + lo] = v;
+    }
+    for (int i = lane; i < n_imp; i += 32) {
+        const float v = zsm[i];
+        int lo = 0, hi = s1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (zc[mid] <= v) lo = mid + 1; else hi = mid; }
+        osm[i + lo] = v;
+    }
+    __syncwarp();
+    float* out = a.z_merged + (size_t)ray * tot;
+    if ((tot & 3) == 0 && (a.warp_floats & 3) == 0) {      // rows are 16-byte aligned: 128-bit stores
+        for (int j = lane; j < (tot >> 2); j += 32) reinterpret_cast<float4*>(out)[j] = reinterpret_cast<const float4*>(osm)[j];
+    } else {
+        for (int j = lane; j < tot; j += 32) out[j] = osm[j];
+    }
+}
+
 int launch_pdf(PdfArgs a, void* stream) {
     if (a.n < 0 || a.nb < 2 || a.nb > 1024 || a.n_imp <= 0 || a.n_imp > 1024)
         return fail(INERF_E_SHAPE, "sample_pdf: need 2 <= n_bins <= 1024, 1 <= n_imp <= 1024");
@@ -245,4 +380,26 @@ extern "C" int inerf_importance_sample(const float* z_coarse, const float* w_coa
     a.z_samples = z_samples; a.inds = (long long*)inds;
     a.z_coarse = z_coarse; a.s1 = s1; a.z_merged = z_merged; a.z_std = z_std;
     return launch_pdf(a, stream);
+}
+
+extern "C" int inerf_importance_sample_rng(const float* z_coarse, const float* w_coarse, int n, int s1, int n_imp,
+                                           const uint64_t* rng_state, uint32_t stream_id, float* z_samples, float* z_merged,
+                                           float* z_std, void* stream) {
+    if (n < 0 || s1 < 3 || s1 > 1024 || n_imp <= 0 || n_imp > 1024) return fail(INERF_E_SHAPE, "inerf_importance_sample_rng: need 3 <= s1 <= 1024, 1 <= n_imp <= 1024");
+    if (stream_id > 255) return fail(INERF_E_ARG, "inerf_importance_sample_rng: stream_id must be < 256");
+    if (n == 0) return INERF_OK;
+    if (!z_coarse || !w_coarse || !rng_state || !z_merged) return fail(INERF_E_ARG, "inerf_importance_sample_rng: NULL pointer");
+    PdfRngArgs a{};
+    a.z_coarse = z_coarse; a.w_coarse = w_coarse; a.n = n; a.s1 = s1; a.n_imp = n_imp;
+    a.rng_state = reinterpret_cast<const unsigned long long*>(rng_state); a.stream_id = stream_id;
+    a.z_samples = z_samples; a.z_merged = z_merged; a.z_std = z_std;
+    const int nb = s1 - 1;
+    a.warp_floats = ((s1 + 3) & ~3) + 2 * ((nb + 3) & ~3) + ((n_imp + 3) & ~3) + ((s1 + n_imp + 3) & ~3);
+    a.runs = (((n_imp + 31) >> 5) + 3) >> 2;
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * a.warp_floats * sizeof(float) > 48 * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * a.warp_floats * sizeof(float);
+    if (smem > 48 * 1024) return fail(INERF_E_SHAPE, "inerf_importance_sample_rng: per-ray working set exceeds 48 KB of shared memory");
+    importance_rng_kernel<<<(n + warps - 1) / warps, warps * 32, smem, as_stream(stream)>>>(a);
+    return check_launch("inerf_importance_sample_rng");
 }

@@ -131,11 +131,12 @@ class _MlpFn(torch.autograd.Function):
         embedded, train = flags
         mode = net._mode()
         pd = [p.detach() for p in params]
-        f = lambda t: None if t is None else ops.f32c(t.detach(), "conditioning")
+        f = lambda t: None if t is None else ops.f32c(t.detach(), "conditioning").reshape(-1)
         aud_d, expr_d, lat_d = f(aud), f(expr), f(latent)
         cond = ops.fold_cond(net._dims, pd, aud_d, expr_d, lat_d)
         if train:
             ctx.net, ctx.has = net, (aud is not None, expr is not None, latent is not None)
+            ctx.cond_shapes = tuple(None if t is None else t.shape for t in (aud, expr, latent))
             if mode == _lib.INERF_MLP_BF16:
                 if embedded:
                     raise NotImplementedError("bf16 training runs through the fused (rays, z) entry; FaceNeRF.forward on embedded rows trains in mlp_mode='fp32'")
@@ -146,8 +147,9 @@ class _MlpFn(torch.autograd.Function):
                 ctx.packed_t = net.packed_weights_bwd(params)
                 net.invalidate_packed()                       # ... and the next inference call must not reuse this step's pack
                 return out
+            net.invalidate_packed()                           # a later bf16 inference call must re-pack: in-place optimiser updates
             out, acts, n_points = ops.mlp_fwd_train(net._dims, pd, cond, x=a) if embedded else \
-                ops.mlp_fwd_train(net._dims, pd, cond, rays=a, z=b)
+                ops.mlp_fwd_train(net._dims, pd, cond, rays=a, z=b)                                 # do not bump parameter versions
             ctx.n_points, ctx.bf16 = n_points, False
             ctx.save_for_backward(acts, *[t for t in (aud_d, expr_d, lat_d) if t is not None], *pd)
             return out
@@ -171,7 +173,8 @@ class _MlpFn(torch.autograd.Function):
         else:
             grads, d_cond = ops.mlp_bwd(d, params, aud, expr, latent, acts, g, ctx.n_points)
         da, de = d.dim_aud, d.dim_expr
-        g_aud = d_cond[:da] if aud is not None else None
-        g_expr = d_cond[da:da + de] if expr is not None else None
-        g_lat = d_cond[da + de:da + de + d.dim_latent] if latent is not None else None
+        sh = ctx.cond_shapes                                  # the conditioning vectors may arrive as (C,), (1, C), ...: same shape back
+        g_aud = d_cond[:da].view(sh[0]) if aud is not None else None
+        g_expr = d_cond[da:da + de].view(sh[1]) if expr is not None else None
+        g_lat = d_cond[da + de:da + de + d.dim_latent].view(sh[2]) if latent is not None else None
         return (None, None, None, None, g_aud, g_expr, g_lat, *grads)

@@ -94,6 +94,21 @@ def get_rays_packed(H, W, focal, c2w, near, far, cx=None, cy=None):
     return rays
 
 
+def get_rays_range(H, W, focal, c2w, near, far, first, count, cx=None, cy=None):
+    """(count, 11) packed rays of the pixels [first, first + count) of the frame: get_rays_packed(...)[first:first + count] without
+    generating the rest of the frame (one rank's band when a frame's rays are sharded over several GPUs)."""
+    c2w = f32c(c2w, "c2w")
+    if c2w.dim() != 2 or c2w.shape[0] < 3 or c2w.shape[1] != 4:
+        raise ValueError("c2w must be (3,4) or (4,4)")
+    cx = W * .5 if cx is None else cx
+    cy = H * .5 if cy is None else cy
+    rays = torch.empty((count, 11), device=c2w.device, dtype=torch.float32)
+    with torch.cuda.device(c2w.device):
+        call("inerf_get_rays_range", _lib.lib().inerf_get_rays_range, H, W, float(focal), float(cx), float(cy), ptr(c2w), 4, float(near),
+             float(far), int(first), int(count), ptr(rays), stream())
+    return rays
+
+
 def get_rays_at(coords, focal, c2w, near, far, cx, cy):
     """(n, 11) packed rays of the selected pixels; coords (n, 2) int64 = (row, col).  Same bits as get_rays_packed(...)[row * W + col]."""
     _need_cuda(coords, "coords")
@@ -148,6 +163,79 @@ def sample_coarse(rays, n_samples, t_rand=None, lindisp=False):
         call("inerf_sample_coarse", _lib.lib().inerf_sample_coarse, ptr(rays), n, rays.shape[1], n_samples, ptr(t_vals), ptr(t_rand),
                                              int(bool(lindisp)), ptr(z), stream())
     return z
+
+
+# ------------------------------------------------------------------------------------------------
+# in-kernel random draws (perturb > 0): Philox state per device, {seed, offset} in device memory
+# ------------------------------------------------------------------------------------------------
+RNG_STREAM_COARSE, RNG_STREAM_PDF = 1, 2
+_rng_states = {}
+
+
+def rng_state(device):
+    """The (2,) int64 device tensor {seed, offset} the *_rng kernels read.  Seeded from torch's generator on first use
+    (torch.manual_seed before the first stochastic render makes a run reproducible); `seed_rng` re-seeds explicitly."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _rng_states.get(key)
+    if st is None:
+        st = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=torch.device("cuda", key))
+        _rng_states[key] = st
+    return st
+
+
+def seed_rng(seed, device=None, offset=0):
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    rng_state(dev).copy_(torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, int(offset)], dtype=torch.int64))
+
+
+def rng_advance(state, increment=1):
+    """offset += increment on the device (one tiny launch; graph-capturable): the next stochastic call draws fresh numbers."""
+    with torch.cuda.device(state.device):
+        call("inerf_rng_advance", _lib.lib().inerf_rng_advance, ptr(state), int(increment), stream())
+
+
+def sample_coarse_rng(rays, n_samples, state=None, lindisp=False, advance=True):
+    """Stratified depths with the jitter drawn in the kernel (audio_exp_nerf.py:321-328 without the torch.rand tensor)."""
+    rays = f32c(rays, "rays")
+    n = rays.shape[0]
+    state = rng_state(rays.device) if state is None else state
+    t_vals = linspace_table(n_samples, rays.device)
+    z = torch.empty((n, n_samples), device=rays.device, dtype=torch.float32)
+    with torch.cuda.device(rays.device):
+        call("inerf_sample_coarse_rng", _lib.lib().inerf_sample_coarse_rng, ptr(rays), n, rays.shape[1], n_samples, ptr(t_vals), ptr(state),
+             int(bool(lindisp)), ptr(z), stream())
+    if advance:
+        rng_advance(state)
+    return z
+
+
+def importance_sample_rng(z_coarse, w_coarse, n_importance, state=None, stream_id=RNG_STREAM_PDF, want_samples=False, advance=True):
+    """importance_sample for perturb > 0 with u ~ U[0,1) drawn in the kernel as sorted order statistics (helper.py:282-283 without the
+    torch.rand tensor and without a sort).  Returns (z_samples|None, z_merged, z_std)."""
+    z_coarse, w_coarse = f32c(z_coarse.detach(), "z_vals"), f32c(w_coarse.detach(), "weights")
+    n, s1 = z_coarse.shape
+    dev = z_coarse.device
+    state = rng_state(dev) if state is None else state
+    zs = torch.empty((n, n_importance), device=dev) if want_samples else None
+    zm = torch.empty((n, s1 + n_importance), device=dev)
+    zstd = torch.empty((n,), device=dev)
+    with torch.cuda.device(dev):
+        call("inerf_importance_sample_rng", _lib.lib().inerf_importance_sample_rng, ptr(z_coarse), ptr(w_coarse), n, s1, n_importance,
+             ptr(state), int(stream_id), ptr(zs), ptr(zm), ptr(zstd), stream())
+    if advance:
+        rng_advance(state)
+    return zs, zm, zstd
+
+
+def flag_nonfinite(tensors, flags):
+    """OR bit i into the int32 device scalar `flags` when tensors[i] holds a NaN / Inf; ONE launch, no host synchronisation."""
+    tensors = [f32c(t, "tensor") for t in tensors]
+    k = len(tensors)
+    xs = (ctypes.c_void_p * k)(*[t.data_ptr() for t in tensors])
+    ns = (ctypes.c_int64 * k)(*[t.numel() for t in tensors])
+    with torch.cuda.device(flags.device):
+        call("inerf_flag_nonfinite", _lib.lib().inerf_flag_nonfinite, xs, ns, k, ptr(flags), stream())
+    return flags
 
 
 # ------------------------------------------------------------------------------------------------

@@ -69,14 +69,18 @@ def _render_rays_impl(rays, bc_rgb, net_coarse, net_fine, aud, expr, latent, N_s
     N_rays = rays.shape[0]
     rays_d = rays[:, 3:6]                                    # strided view; the kernels take the row stride
 
-    t_rand = None
-    if perturb > 0.:
-        if pytest:                                           # :323-325
+    # perturb > 0: the reference draws torch.rand(N, S) / torch.rand(N, N_importance) from the global generator (:321-328, helper.py:282);
+    # here the draws are made inside the sampling kernels (Philox, ops.rng_state) unless pytest=True asks for the numpy-seeded tables
+    in_kernel_rng = perturb > 0. and not pytest
+    if in_kernel_rng:
+        rng = ops.rng_state(rays.device)
+        z_vals = ops.sample_coarse_rng(rays, N_samples, rng, lindisp, advance=False)
+    else:
+        t_rand = None
+        if perturb > 0.:                                     # :323-325
             np.random.seed(0)
             t_rand = torch.Tensor(np.random.rand(N_rays, N_samples)).to(rays.device)
-        else:
-            t_rand = torch.rand((N_rays, N_samples), device=rays.device)
-    z_vals = ops.sample_coarse(rays, N_samples, t_rand, lindisp)
+        z_vals = ops.sample_coarse(rays, N_samples, t_rand, lindisp)
 
     raw = net_coarse.query(rays, z_vals, aud, expr, latent)
     outs = ops.composite(raw, z_vals, rays_d, bc_rgb, _noise(raw, raw_noise_std, pytest), white_bkgd, with_fg)
@@ -87,15 +91,17 @@ def _render_rays_impl(rays, bc_rgb, net_coarse, net_fine, aud, expr, latent, N_s
         rgb_map_0, disp_map_0, acc_map_0 = rgb_map, disp_map, acc_map
         outs0 = outs
         det = (perturb == 0.)
-        if pytest:                                           # helper.py:285-293
-            np.random.seed(0)
-            u = (torch.Tensor(np.linspace(0., 1., N_importance)) if det
-                 else torch.Tensor(np.random.rand(N_rays, N_importance))).to(rays.device)
-        elif det:
-            u = ops.linspace_table(N_importance, rays.device)
+        if in_kernel_rng:
+            _, z_vals, z_std = ops.importance_sample_rng(z_vals, weights, N_importance, rng, advance=False)
+            ops.rng_advance(rng)                             # one bump per render_rays call; the two kernels use different streams
         else:
-            u = torch.rand((N_rays, N_importance), device=rays.device)
-        z_samples, z_vals, z_std, _ = ops.importance_sample(z_vals, weights, u, pdf_policy)
+            if pytest:                                       # helper.py:285-293
+                np.random.seed(0)
+                u = (torch.Tensor(np.linspace(0., 1., N_importance)) if det
+                     else torch.Tensor(np.random.rand(N_rays, N_importance))).to(rays.device)
+            else:
+                u = ops.linspace_table(N_importance, rays.device)
+            z_samples, z_vals, z_std, _ = ops.importance_sample(z_vals, weights, u, pdf_policy)
 
         run_fn = net_coarse if net_fine is None else net_fine
         raw = run_fn.query(rays, z_vals, aud, expr, latent)
@@ -116,17 +122,26 @@ def _render_rays_impl(rays, bc_rgb, net_coarse, net_fine, aud, expr, latent, N_s
         if with_fg:
             ret['last_weight0'] = outs0[3][..., -1]
             ret['rgb_map_fg0'] = outs0[5]
-    if check_numerics:                                       # the reference does 9 host syncs here (:367-369)
-        bad = [k for k in ret if not bool(torch.isfinite(ret[k]).all())]
-        for k in bad:
-            logger.info(f"! [Numerical Error] {k} contains nan or inf.")
+    if in_kernel_rng and not N_importance > 0:
+        ops.rng_advance(rng)
+    if check_numerics:
+        # the reference scans every output with .any() -- nine host synchronisations per call (:367-369); here ONE kernel ORs a bit per
+        # tensor into a device flag and the host reads that flag once
+        keys = list(ret)
+        flag = torch.zeros((1,), dtype=torch.int32, device=rays.device)
+        ops.flag_nonfinite([ret[k] for k in keys], flag)
+        bits = int(flag.item())
+        for i, k in enumerate(keys):
+            if bits >> i & 1:
+                logger.info(f"! [Numerical Error] {k} contains nan or inf.")
+        ret['_nonfinite'] = [k for i, k in enumerate(keys) if bits >> i & 1]
     ret['_z_vals'] = z_vals
     ret['_weights'] = weights
     ret['_depth_map'] = depth_map
     return ret
 
 
-_PRIVATE = ('_z_vals', '_weights', '_depth_map')
+_PRIVATE = ('_z_vals', '_weights', '_depth_map', '_nonfinite')
 
 
 def render_rays(ray_batch, bc_rgb, aud_para, network_fn, network_query_fn=None, N_samples=64, retraw=False,

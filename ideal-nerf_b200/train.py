@@ -26,6 +26,7 @@ class FlatParams:
             raise ValueError("FlatParams: no parameters")
         dev, dt = self.params[0].device, self.params[0].dtype
         offs, o = [], 0
+        self.offsets = offs
         for p in self.params:
             if p.device != dev or p.dtype != dt:
                 raise ValueError("FlatParams: parameters must share device and dtype")
@@ -70,7 +71,11 @@ def learning_rate(args, global_step):
 
 
 class TrainStep:
-    """One call = one iteration of the reference's inner loop for a ray batch already on the device."""
+    """One call = one iteration of the reference's inner loop for a ray batch already on the device.
+
+    The optimiser is ONE Adam over the flat buffer; `optimizer_state_dict()` / `load_optimizer_state_dict()` convert to and from the
+    reference's per-parameter Adam state (params = list(network.parameters()) + [latent_codes], audio_exp_nerf.py:487-493) so the
+    'optimizer' entry of head.tar moves both ways; `save()` / `load()` write and resume the reference's checkpoint (:516-525, :584-591)."""
 
     def __init__(self, network, latent_codes, args, world=1, group=None):
         self.net, self.latent_codes, self.args, self.world, self.group = network, latent_codes, args, world, group
@@ -78,6 +83,74 @@ class TrainStep:
         self.flat = FlatParams(list(network.parameters()) + [latent_codes])
         self.optimizer = torch.optim.Adam([self.flat.flat], lr=args.lrate, betas=(0.9, 0.999), fused=latent_codes.is_cuda)
         self.global_step = 0
+
+    # -- checkpoint interchange with the reference's per-parameter Adam -----------------------------------------------------------
+    def optimizer_state_dict(self):
+        """Adam state in the layout torch.optim.Adam(list(network.parameters()) + [latent_codes]) writes: one entry per parameter."""
+        sd = self.optimizer.state_dict()
+        st = sd["state"].get(0)
+        state = {}
+        if st:
+            for i, (p, off) in enumerate(zip(self.flat.params, self.flat.offsets)):
+                n = p.numel()
+                state[i] = {"step": st["step"].detach().clone().cpu(), "exp_avg": st["exp_avg"][off:off + n].view(p.shape).clone(),
+                            "exp_avg_sq": st["exp_avg_sq"][off:off + n].view(p.shape).clone()}
+        group = {k: v for k, v in sd["param_groups"][0].items() if k != "params"}
+        group.update(fused=None, foreach=None, params=list(range(len(self.flat.params))))
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd):
+        """Accepts the per-parameter layout above (the reference's head.tar) or this class's own flat one-parameter layout."""
+        n_par = len(self.flat.params)
+        ids = sd["param_groups"][0]["params"]
+        if len(ids) == 1 and n_par != 1:
+            self.optimizer.load_state_dict(sd)
+            return
+        if len(ids) != n_par:
+            raise ValueError(f"optimizer state has {len(ids)} parameters, this TrainStep has {n_par}")
+        flat = self.flat.flat
+        exp_avg, exp_avg_sq = torch.zeros_like(flat.data), torch.zeros_like(flat.data)
+        step = None
+        for i, (p, off) in enumerate(zip(self.flat.params, self.flat.offsets)):
+            st = sd["state"].get(ids[i])
+            if not st:                                   # a parameter that never received a gradient has no state in the reference
+                continue
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError(f"optimizer state of parameter {i} has shape {tuple(st['exp_avg'].shape)}, expected {tuple(p.shape)}")
+            n = p.numel()
+            exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+            exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            s = float(st["step"])
+            step = s if step is None else max(step, s)
+        group = {k: v for k, v in self.optimizer.state_dict()["param_groups"][0].items()}
+        for k in ("lr", "betas", "eps", "weight_decay", "amsgrad"):
+            if k in sd["param_groups"][0]:
+                group[k] = sd["param_groups"][0][k]
+        state = {} if step is None else {0: {"step": torch.tensor(step, dtype=torch.float32), "exp_avg": exp_avg, "exp_avg_sq": exp_avg_sq}}
+        self.optimizer.load_state_dict({"state": state, "param_groups": [group]})
+
+    def save(self, path):
+        """head.tar as the reference writes it (audio_exp_nerf.py:584-591), loadable by the reference's resume code (:516-525)."""
+        torch.save({"global_step": int(self.global_step), "model_state_dict": self.net.state_dict(),
+                    "optimizer": self.optimizer_state_dict(), "latent_codes": self.latent_codes.data.clone()}, path)
+
+    def load(self, path, map_location=None):
+        """Resume from a head.tar written by the reference or by save(): weights and latent codes are copied IN PLACE (they are views of
+        the flat Adam buffer), the Adam moments are scattered into the flat state, global_step and the learning rate are restored."""
+        ckpt = torch.load(path, map_location=map_location, weights_only=False)
+        self.net.load_state_dict(ckpt["model_state_dict"])                 # nn.Module.load_state_dict copies in place
+        with torch.no_grad():
+            self.latent_codes.data.copy_(ckpt["latent_codes"].to(self.latent_codes.device))
+        self.global_step = int(ckpt.get("global_step", 0))
+        if ckpt.get("optimizer") is not None:
+            self.load_optimizer_state_dict(ckpt["optimizer"])              # carries the learning rate the schedule had reached (:554-558)
+        else:
+            for g in self.optimizer.param_groups:                          # the lr in force at step k is the one set after step k-1
+                g["lr"] = learning_rate(self.args, self.global_step - 1) if self.global_step > 0 else self.args.lrate
+        for m in self.net.modules():
+            if hasattr(m, "invalidate_packed"):
+                m.invalidate_packed()
+        return self.global_step
 
     def __call__(self, rays, bc_rgb, target, aud_feature, expr, index, perturb=None):
         a = self.args
@@ -89,6 +162,8 @@ class TrainStep:
         loss.backward()
         self.flat.gather_grads(self.world, self.group)
         self.optimizer.step()
+        for m in (self.net.face_nerf_coarse, self.net.face_nerf_fine):      # fused Adam does not bump parameter versions
+            m.invalidate_packed()
         lr = learning_rate(a, self.global_step)
         for g in self.optimizer.param_groups:
             g["lr"] = lr

@@ -91,6 +91,11 @@ int inerf_get_rays(int H, int W, float focal, float cx, float cy, const float* c
 int inerf_get_rays_at(const int64_t* coords, int n, float focal, float cx, float cy, const float* c2w, int c2w_row_stride,
                       float near_, float far_, float* rays, void* stream);
 
+/* The same rays for the pixels [first, first + count) of the row-major H x W grid only (one rank's band of a frame whose rays are
+ * sharded over several GPUs: SURVEY.md 8e).  rays: (count, 11); rays[0] is pixel `first`.  Same bits as inerf_get_rays. */
+int inerf_get_rays_range(int H, int W, float focal, float cx, float cy, const float* c2w, int c2w_row_stride,
+                         float near_, float far_, int first, int count, float* rays, void* stream);
+
 /* Ray packing from caller-supplied origins/directions (training batches).
  * Replaces audio_exp_nerf.py:409-427.  rays_o, rays_d: (n,3); rays: (n,11). */
 int inerf_pack_rays(const float* rays_o, const float* rays_d, int n, float near_, float far_, float* rays,
@@ -110,6 +115,27 @@ int inerf_to8b(const float* x, int64_t n, uint8_t* out, void* stream);
  * column is forced to 1.0 as the reference does at :326.  z: (n, s). */
 int inerf_sample_coarse(const float* rays, int n, int ray_stride, int s, const float* t_vals,
                         const float* t_rand, int lindisp, float* z, void* stream);
+
+/* ---- in-kernel random draws (perturb > 0) ---------------------------------------------------
+ * The stochastic branches of render_rays draw with torch.rand from the global generator (audio_exp_nerf.py:321-328: the
+ * stratified jitter; helper.py:282-283: the inverse-CDF draws).  The *_rng entry points make those draws inside the kernel with
+ * Philox4x32-10, so no (N, S) tensor of draws is written to and read back from HBM and the whole step can live in a CUDA graph.
+ * rng_state: DEVICE pointer to two uint64 {seed, offset}; counter = (draw index, offset + (stream_id << 56)), key = seed.
+ * inerf_rng_advance adds `increment` to the offset (one tiny launch, graph-capturable) so the next step draws fresh numbers. */
+#define INERF_RNG_STREAM_COARSE 1u /* stratified jitter of inerf_sample_coarse_rng */
+#define INERF_RNG_STREAM_PDF 2u    /* default stream of inerf_importance_sample_rng */
+int inerf_rng_advance(uint64_t* rng_state, uint64_t increment, void* stream);
+
+/* inerf_sample_coarse with t_rand = U[0,1) drawn in the kernel (word (i & 3) of Philox block (i >> 2), i = ray * s + sample; the
+ * last sample of every ray uses 1.0 as the reference does at :326). */
+int inerf_sample_coarse_rng(const float* rays, int n, int ray_stride, int s, const float* t_vals, const uint64_t* rng_state,
+                            int lindisp, float* z, void* stream);
+
+/* NaN / Inf scan of up to INERF_MAX_SCAN tensors in ONE launch: bit i of *flags is OR-ed in when xs[i] (ns[i] floats) holds a
+ * non-finite value.  Replaces the nine `.any()` host synchronisations of audio_exp_nerf.py:367-369 with a device flag the caller
+ * reads once (or never).  xs_host / ns_host: HOST arrays of k device pointers / element counts; flags: DEVICE int32, not cleared. */
+#define INERF_MAX_SCAN 16
+int inerf_flag_nonfinite(const float* const* xs_host, const int64_t* ns_host, int k, int32_t* flags, void* stream);
 
 /* ---- compositing ---------------------------------------------------------------------------- */
 
@@ -160,6 +186,14 @@ int inerf_sample_pdf(const float* bins, int bins_stride, const float* weights, i
 int inerf_importance_sample(const float* z_coarse, const float* w_coarse, int n, int s1, int n_imp,
                             const float* u, int u_per_ray, int policy, float* z_samples, int64_t* inds,
                             float* z_merged, float* z_std, void* stream);
+
+/* inerf_importance_sample for the stochastic branch (perturb > 0, helper.py:282-283) with the draws made in the kernel: the ORDER
+ * STATISTICS of n_imp iid U[0,1) per ray are generated directly (exponential spacings), so z_samples come out ascending and no sort
+ * is needed; the CDF is a plain fp32 warp scan (bit-exactness against torch-CPU is only defined for det=True / supplied draws, which
+ * stay with inerf_importance_sample).  z_samples may be NULL (the renderer only consumes z_merged and z_std). */
+int inerf_importance_sample_rng(const float* z_coarse, const float* w_coarse, int n, int s1, int n_imp,
+                                const uint64_t* rng_state, uint32_t stream_id, float* z_samples, float* z_merged,
+                                float* z_std, void* stream);
 
 /* ---- FaceNeRF MLP --------------------------------------------------------------------------- */
 

@@ -16,7 +16,22 @@ import sys
 import tempfile
 import types
 
-REF_ROOT = os.environ.get("IDEAL_NERF_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    """$IDEAL_NERF_REFERENCE, else /root/reference (build container), else oracle/_ref (the copy oracle/make_ref.py made; GPU box)."""
+    for p in (os.environ.get("IDEAL_NERF_REFERENCE"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if p and os.path.isdir(os.path.join(p, "NeRFs")):
+            return p
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
+
+
+def available():
+    return os.path.isdir(os.path.join(REF_ROOT, "NeRFs"))
 
 NEAR = 0.5772005200386048   # NeRFs/HeadNeRF/configs/audio_expr_nerf/may/paper_model/torso_bg.txt:11
 FAR = 1.1772005200386046    # ...:12
@@ -44,13 +59,15 @@ def _stub_modules():
 
 
 def import_head(perturb=0.0, n_samples=64, n_importance=128, dim_aud=64, dim_expr=76,
-                near=NEAR, far=FAR):
-    """Return the reference module NeRFs.HeadNeRF.train.audio_exp_nerf (class-form renderer)."""
+                near=NEAR, far=FAR, force_cpu=False):
+    """Return the reference module NeRFs.HeadNeRF.train.audio_exp_nerf (class-form renderer).  force_cpu: keep the reference's
+    hard-coded `.cuda()` calls (helper.py:191,197,204,279,282) on the host even when a GPU is visible (CPU baseline on the GPU box);
+    without it, on a GPU box, call torch.set_default_tensor_type('torch.cuda.FloatTensor') first like the reference's __main__ (:598)."""
     import torch
-    if not os.path.isdir(REF_ROOT):
+    if not available():
         raise RuntimeError(f"reference tree not found at {REF_ROOT}")
     _stub_modules()
-    if not torch.cuda.is_available():
+    if force_cpu or not torch.cuda.is_available():
         torch.Tensor.cuda = lambda self, *a, **k: self
     vis = tempfile.mkdtemp(prefix="inerf_vis_")
     sys.argv = ["ref", "--N_samples", str(n_samples), "--N_importance", str(n_importance),

@@ -453,21 +453,29 @@ def _psnr(a, b):
 
 @pytest.mark.parametrize("tag", ["init", "dense"])
 def test_render_rays_bf16_psnr_gate(M, golden, tag):
-    """3072 rays, 64+128 samples in bf16-MLP mode against the reference's outputs: PSNR delta <= 0.05 dB."""
+    """3072 rays, 64+128 samples in bf16-MLP mode against the GOLDEN outputs of the unmodified reference.  north_star gate: PSNR delta
+    <= 0.05 dB.  The 'ground truth' the PSNRs are taken against sits 30 dB from the reference render (reference + N(0, 0.0316^2) noise,
+    seeded), where the gate is sensitive: an rms error of 3.4e-3 between the two renders (49 dB) already moves the PSNR by 0.05 dB;
+    against the U[0,1) target of the fixture (8 dB away) errors ten times larger would pass."""
     g = golden("render_3072")
     net = _preset_nets(M, g, tag, mode="bf16")
     rays, bc = C(g["rays"]), C(g["bc_rgb"])
     with torch.no_grad():
         r = net.render_rays(rays, bc, C(g["aud"]), None, C(g["latent"]), C(g["expr"]), perturb=0.)
-    ref = torch.from_numpy(g[f"{tag}_rgb_map"]).to(DEV)
-    tgt = torch.from_numpy(g["target"]).to(DEV)
-    psnr_ref, psnr_ours = _psnr(ref, tgt), _psnr(r["rgb_map"], tgt)
-    print(f"[{tag}] PSNR vs target: reference {psnr_ref:.4f} dB, bf16 {psnr_ours:.4f} dB; "
-          f"PSNR(bf16 vs reference render) {_psnr(r['rgb_map'], ref):.2f} dB; max-abs {maxabs(r['rgb_map'], ref):.3e}; "
-          f"acc max-abs {maxabs(r['acc_map'], g[f'{tag}_acc_map']):.3e}")
-    assert abs(psnr_ours - psnr_ref) <= 0.05, "north_star gate: PSNR delta <= 0.05 dB in bf16-MLP mode"
-    assert _psnr(r["rgb_map"], ref) >= 35.0
-    assert abs(_psnr(r["rgb0"], tgt) - _psnr(torch.from_numpy(g[f"{tag}_rgb0"]).to(DEV), tgt)) <= 0.05
+    gen = torch.Generator(device=DEV).manual_seed(30)
+    for key in ("rgb_map", "rgb0"):
+        ref = torch.from_numpy(g[f"{tag}_{key}"]).to(DEV)
+        tgt = ref + 0.0316 * torch.randn(ref.shape, device=DEV, generator=gen)
+        psnr_ref, psnr_ours, between, mx = _psnr(ref, tgt), _psnr(r[key], tgt), _psnr(r[key], ref), maxabs(r[key], ref)
+        print(f"[{tag}] {key}: PSNR vs target: reference {psnr_ref:.4f} dB, bf16 {psnr_ours:.4f} dB (delta {abs(psnr_ours - psnr_ref):.4f}); "
+              f"PSNR(bf16, reference render) {between:.2f} dB; max-abs {mx:.3e}")
+        assert 29.5 < psnr_ref < 30.5
+        assert abs(psnr_ours - psnr_ref) <= 0.05, "north_star gate: PSNR delta <= 0.05 dB in bf16-MLP mode"
+        # the render itself: random-init weights amplify nothing (bf16 operand rounding ~3e-4 on the image); the normalised-density preset
+        # scales sigma by ~100, there the bf16 render sits ~54 dB from the reference (CPU emulation of the kernel's rounding points)
+        assert between >= (70.0 if tag == "init" else 47.0), between
+        assert mx <= (3e-3 if tag == "init" else 6e-2), mx
+    print(f"[{tag}] acc max-abs {maxabs(r['acc_map'], g[f'{tag}_acc_map']):.3e}")
 
 
 def test_bf16_rejects_small_s_and_embedded(M):
@@ -763,35 +771,6 @@ def test_bf16_training_loop_reduces_loss(M):
     assert abs(losses["bf16"][-1] - losses["fp32"][-1]) <= 0.05 * abs(losses["fp32"][0]), "bf16 and fp32 training must track each other"
 
 
-@pytest.mark.parametrize("n,s", [(1, 64), (3, 43), (8, 64), (301, 64), (47, 45), (333, 192)])
-def test_bf16_pair_kernel_v2_bit_matches_v1(M, n, s):
-    """The experimental cta_group::2 kernel (csrc/mlp_bf16_v2.cu, INERF_MLP_V2=1: CTA pairs, M = 256 MMAs over the whole layer width,
-    slots alternating, remote mbarrier arrivals) reads the same packed blob and bias tiles and must return the same bits as v1,
-    including chunks past the end of a ragged input (one CTA of the last pair idles on clamped points)."""
-    b = O.synthetic_train_batch(0)
-    rays = b["rays"][:n].to(DEV)
-    net = head_net(M, O.init_face_nerf(7), "bf16")
-    aud, expr, lat = b["aud"].to(DEV), b["expr"].to(DEV), b["latent"].to(DEV)
-    z = M.ops.sample_coarse(rays, s, torch.rand(n, s, device=DEV, generator=torch.Generator(device=DEV).manual_seed(s)))
-    old = os.environ.pop("INERF_MLP_V2", None)
-    try:
-        with torch.no_grad():
-            r1 = net.query(rays, z, aud, expr, lat)
-            os.environ["INERF_MLP_V2"] = "1"
-            r2 = net.query(rays, z, aud, expr, lat)
-    finally:
-        os.environ.pop("INERF_MLP_V2", None)
-        if old is not None:
-            os.environ["INERF_MLP_V2"] = old
-    assert torch.isfinite(r2).all()
-    assert torch.equal(r1, r2)
-    # and both against the fp32 kernel (tiny inputs: fewer points than one 256-point iteration, one slot entirely past the end)
-    n32 = head_net(M, O.init_face_nerf(7), "fp32")
-    with torch.no_grad():
-        r32 = n32.query(rays, z, aud, expr, lat)
-    close(r1, r32, 3e-2 * max(1.0, float(r32.abs().max())), "bf16 vs fp32 raw")
-
-
 def test_to8b_and_video_driver(M):
     """to8b bit-for-bit against numpy (helper.py:154, incl. out-of-range / NaN-free edge values and a ragged length), and the video
     driver: frames rendered, converted on the device and copied asynchronously == to8b(render_dynamic_face) frame by frame."""
@@ -1063,3 +1042,191 @@ def test_head_torso_composite_bf16_mode(M):
     for a, b_ in zip(out["fp32"], out["bf16"]):
         print(f"head+torso bf16 vs fp32: max-abs {float((a - b_).abs().max()):.3e}  PSNR {_psnr(a, b_):.1f} dB")
         assert _psnr(a, b_) >= 35.0
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: band rays, in-kernel Philox draws, NaN flag, config 4 at frame size, long bf16-vs-fp32 training run
+# ------------------------------------------------------------------------------------------------
+def test_get_rays_range_equals_full_frame_slice(M):
+    cam = O.synthetic_camera()
+    c2w = cam["c2w"].to(DEV)
+    full = M.ops.get_rays_packed(450, 450, cam["focal"], c2w, O.NEAR, O.FAR)
+    for first, count in ((0, 450), (101337, 25313), (202500 - 7, 7), (5, 0)):
+        part = M.ops.get_rays_range(450, 450, cam["focal"], c2w, O.NEAR, O.FAR, first, count)
+        assert part.shape == (count, 11) and bits_equal(part, full[first:first + count])
+    with pytest.raises(RuntimeError, match="outside the frame"):
+        M.ops.get_rays_range(450, 450, cam["focal"], c2w, O.NEAR, O.FAR, 202500 - 3, 4)
+
+
+@pytest.mark.parametrize("lindisp", [False, True])
+def test_sample_coarse_rng_bit_exact_vs_philox_oracle(M, lindisp):
+    """The in-kernel stratified jitter == the supplied-draws kernel fed with the numpy restatement of Philox4x32-10 (oracle/philox_ref.py)
+    for the same (seed, offset): bit-exact, including a second call after inerf_rng_advance."""
+    from oracle import philox_ref as P
+    b = O.synthetic_train_batch(0)
+    n, s = 777, 64
+    rays = b["rays"][:n].to(DEV)
+    st = torch.tensor([0x1234567 + (5 << 32), 40], dtype=torch.int64, device=DEV)
+    for k in range(2):
+        z = M.ops.sample_coarse_rng(rays, s, st, lindisp, advance=True)
+        u = torch.from_numpy(P.draws_u01(0x1234567 + (5 << 32), 40 + k, 1, n * s)).reshape(n, s)
+        want = M.ops.sample_coarse(rays, s, u.to(DEV), lindisp)
+        assert bits_equal(z, want), f"call {k}"
+        assert bits_equal(want.cpu(), O.stratified_z(b["rays"][:n, 6:7], b["rays"][:n, 7:8], s, n, u, lindisp))
+    assert st.tolist() == [0x1234567 + (5 << 32), 42]
+    assert M.ops.sample_coarse_rng(rays[:0], s, st).shape == (0, s)
+
+
+def test_importance_sample_rng_properties(M, golden):
+    """The stochastic importance sampler (draws made in the kernel as sorted uniforms): z_merged is sorted and is exactly the multiset
+    z_coarse + z_samples; z_std matches the samples; the same (seed, offset) reproduces the call, an advanced offset does not; the
+    samples follow the pdf -- flat weights give uniform samples over the bins, a spike collects them, and on the render fixture's coarse
+    weights the per-bin sample counts match the deterministic inverse-CDF counts of the reference's det=True pass in expectation."""
+    g = golden("render_3072")
+    b = O.synthetic_train_batch(0)
+    n, s1, n_imp = 3072, 64, 128
+    z = M.ops.sample_coarse(b["rays"].to(DEV), s1)
+    w = C(g["dense_w0_all"])
+    st = torch.tensor([99, 0], dtype=torch.int64, device=DEV)
+    zs, zm, zstd = M.ops.importance_sample_rng(z, w, n_imp, st, want_samples=True, advance=False)
+    assert zs.shape == (n, n_imp) and zm.shape == (n, s1 + n_imp)
+    assert bool((zm[:, 1:] >= zm[:, :-1]).all()) and bool((zs[:, 1:] >= zs[:, :-1]).all())
+    assert bits_equal(zm, torch.sort(torch.cat([z, zs], -1), -1)[0])
+    close(zstd, zs.std(-1, unbiased=False), 1e-6, "z_std")
+    zs2, zm2, _ = M.ops.importance_sample_rng(z, w, n_imp, st, want_samples=True, advance=True)
+    assert bits_equal(zs, zs2) and bits_equal(zm, zm2)
+    zs3, _, _ = M.ops.importance_sample_rng(z, w, n_imp, st, want_samples=True, advance=False)
+    assert not torch.equal(zs, zs3) and st.tolist() == [99, 1]
+    _, zm4, _ = M.ops.importance_sample_rng(z, w, n_imp, st, want_samples=False, advance=False)      # z_samples is optional
+    assert bits_equal(zm4, torch.sort(torch.cat([z, zs3], -1), -1)[0])
+    # distribution: per-bin sample mass == pdf mass (averaged over 3072 rays x 128 draws)
+    mid = .5 * (z[:, 1:] + z[:, :-1])
+    pdf = (w[:, 1:-1] + 1e-5) / (w[:, 1:-1] + 1e-5).sum(-1, keepdim=True)
+    bin_of = (torch.searchsorted(mid.contiguous(), zs.contiguous(), right=True) - 1).clamp(0, s1 - 3)
+    cnt = torch.zeros(n, s1 - 2, device=DEV).scatter_add_(1, bin_of, torch.ones_like(zs)) / n_imp
+    err = float((cnt.mean(0) - pdf.mean(0)).abs().max())
+    print(f"importance_sample_rng: max |mean sample mass - mean pdf mass| over the 62 bins = {err:.2e}")
+    assert err < 2e-3
+    # flat pdf -> uniform over [mid_0, mid_62]; spike -> every sample inside the spike's bin
+    flat = torch.zeros(n, s1, device=DEV)
+    zsf, _, _ = M.ops.importance_sample_rng(z, flat, n_imp, st, want_samples=True)
+    t = (zsf - mid[:, :1]) / (mid[:, -1:] - mid[:, :1])
+    assert abs(float(t.mean()) - 0.5) < 2e-3 and abs(float(t.var()) - 1 / 12) < 2e-3 and 0.0 <= float(t.min()) and float(t.max()) <= 1.0
+    spike = torch.zeros(n, s1, device=DEV); spike[:, 18] = 1.0
+    zss, _, _ = M.ops.importance_sample_rng(z, spike, n_imp, st, want_samples=True)
+    inside = ((zss >= mid[:, 17:18]) & (zss <= mid[:, 18:19])).float().mean()      # weights[..., 1:-1][17] spans [mid_17, mid_18]
+    assert float(inside) > 0.998
+    # ragged shapes
+    for s1_, n_imp_ in ((7, 5), (45, 130), (64, 1)):
+        zc = torch.sort(torch.rand(33, s1_, device=DEV), -1)[0]
+        zs_, zm_, zstd_ = M.ops.importance_sample_rng(zc, torch.rand(33, s1_, device=DEV), n_imp_, st, want_samples=True)
+        assert bits_equal(zm_, torch.sort(torch.cat([zc, zs_], -1), -1)[0])
+        close(zstd_, zs_.std(-1, unbiased=False), 1e-6, "z_std ragged")
+
+
+def test_render_rays_stochastic_branch_statistics(M, golden):
+    """perturb = 1 with in-kernel draws: the render is a Monte-Carlo estimate around the det render -- its mean over the rays matches the
+    supplied-draws (pytest=True) render of the same network closely, two calls differ, and torch.manual_seed + seed_rng reproduce one."""
+    g = golden("render_3072")
+    net = _preset_nets(M, g, "dense")
+    rays, bc = C(g["rays"]), C(g["bc_rgb"])
+    args = (rays, bc, C(g["aud"]), None, C(g["latent"]), C(g["expr"]))
+    with torch.no_grad():
+        M.ops.seed_rng(7)
+        a = net.render_rays(*args, perturb=1.0)
+        b = net.render_rays(*args, perturb=1.0)
+        M.ops.seed_rng(7)
+        a2 = net.render_rays(*args, perturb=1.0)
+        d = net.render_rays(*args, perturb=0.)
+    assert bits_equal(a["rgb_map"], a2["rgb_map"]) and not torch.equal(a["rgb_map"], b["rgb_map"])
+    assert abs(float(a["rgb_map"].mean() - d["rgb_map"].mean())) < 5e-3 and abs(float(a["acc0"].mean() - d["acc0"].mean())) < 5e-3
+    assert _psnr(a["rgb_map"], d["rgb_map"]) > 25.0
+
+
+def test_nonfinite_flag(M, golden):
+    x = [torch.zeros(1000, device=DEV), torch.ones(7, 3, device=DEV), torch.zeros(0, device=DEV), torch.ones(300000, device=DEV)]
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    assert int(M.ops.flag_nonfinite(x, flag)) == 0
+    x[1][3, 1] = float("nan"); x[3][299999] = float("inf")
+    assert int(M.ops.flag_nonfinite(x, flag)) == 0b1010
+    # through render_rays: a NaN audio code poisons every output; one launch + one host read instead of nine .any() syncs
+    g = golden("render_3072")
+    net = _preset_nets(M, g, "init")
+    from ideal_nerf_b200.render import _render_rays_impl
+    aud = C(g["aud"]).clone(); aud[3] = float("nan")
+    with torch.no_grad():
+        r = _render_rays_impl(C(g["rays"])[:64], C(g["bc_rgb"])[:64], net.face_nerf_coarse, net.face_nerf_fine, aud, C(g["expr"]), C(g["latent"]),
+                              64, 128, check_numerics=True)
+        ok = _render_rays_impl(C(g["rays"])[:64], C(g["bc_rgb"])[:64], net.face_nerf_coarse, net.face_nerf_fine, C(g["aud"]), C(g["expr"]),
+                               C(g["latent"]), 64, 128, check_numerics=True)
+    assert "rgb_map" in r["_nonfinite"] and ok["_nonfinite"] == []
+
+
+def test_head_torso_frame_band_config4(M):
+    """BASELINE.json config 4 at frame size: the head + torso composited 450 x 450 frame (test_torso.py:516-523; torso rays from the
+    frame-0 camera, train_torso.py:132-134) -- three image rows of the frame against the oracle, fp32 mode, <= 1e-3."""
+    cam, fr = O.synthetic_camera(), O.synthetic_frame(0)
+    args = M.default_args(dim_aud=64, dim_expr=79, perturb=0.)
+    net = M.TorsoNetwork(450, 450, 1200., O.NEAR, O.FAR, 1 << 20, 64, 128, args=args)
+    sds = {"face_nerf_coarse": O.init_face_nerf(21, 64, 79, 32), "face_nerf_fine": O.init_face_nerf(22, 64, 79, 32),
+           "torso_coarse_nerf": O.init_face_nerf(23, 106, 0, 0), "torso_fine_nerf": O.init_face_nerf(24, 106, 0, 0)}
+    gen = torch.Generator().manual_seed(4)
+    aud, expr, lat = fr["aud"], torch.randn(79, generator=gen), fr["latent"]
+    pose = cam["c2w"].clone(); pose[:3, 3] += torch.tensor([0.01, -0.02, 0.0])          # this frame's head pose
+    pose0 = cam["c2w"]                                                                  # frame-0 camera of the torso rays
+    et = O.pose_to_euler_trans(pose[None])
+    sig = torch.cat([aud[:64], O.positional_encoding(et[:, :3], 3).squeeze(0), O.positional_encoding(et[:, 3:], 3).squeeze(0)])
+    ro, rd = O.get_rays(450, 450, cam["focal"], pose, cam["cx"], cam["cy"])
+    rays_h_cpu = O.pack_rays(ro.reshape(-1, 3), rd.reshape(-1, 3), O.NEAR, O.FAR)
+    rays_t_cpu = fr["rays"]
+    pre = rays_h_cpu[::397]
+    for k in sds:
+        head = "face" in k
+        sds[k] = O.normalise_density(sds[k], pre if head else rays_t_cpu[::397], aud if head else sig, expr if head else None, lat if head else None)
+        getattr(net, k).load_state_dict(sds[k])
+    net = net.to(DEV).eval()
+    rows = slice(210 * 450, 213 * 450)
+    with torch.no_grad():
+        rays_h = M.ops.get_rays_packed(450, 450, cam["focal"], pose.to(DEV), O.NEAR, O.FAR)
+        rays_t = M.ops.get_rays_packed(450, 450, cam["focal"], pose0.to(DEV), O.NEAR, O.FAR)
+        rgb, rgb0 = net(rays_h, rays_t, fr["bc_rgb"].to(DEV), aud.to(DEV), pose.to(DEV), expr.to(DEV), lat.to(DEV), perturb=0.)
+        assert rgb.shape == (202500, 3) and bool(torch.isfinite(rgb).all())
+        h = O.render_rays(rays_h_cpu[rows], fr["bc_rgb"][rows], sds["face_nerf_coarse"], sds["face_nerf_fine"], aud, expr, lat, with_fg=True)
+        t = O.render_rays(rays_t_cpu[rows], fr["bc_rgb"][rows], sds["torso_coarse_nerf"], sds["torso_fine_nerf"], sig, None, None, with_fg=True)
+    want = O.head_torso_blend(h["rgb_map"], t["last_weight"], t["rgb_map_fg"])
+    assert 0.02 < float(t["last_weight"].mean()) < 0.98, "torso preset must be neither empty nor opaque"
+    close(rgb[rows], want, 1e-3, "config 4 frame band rgb_com")
+    close(rgb0[rows], O.head_torso_blend(h["rgb0"], t["last_weight0"], t["rgb_map_fg0"]), 1e-3, "config 4 frame band rgb_com0")
+
+
+def test_bf16_vs_fp32_training_500_steps(M):
+    """the bf16 tensor-core training kernels against the fp32 kernels over a REAL optimisation run -- 500 Adam steps
+    (lr 3e-4, the reference's loss and schedule, train.TrainStep) on N_rand = 3072 rays towards the render of a teacher network, same
+    initial weights, deterministic depths (perturb = 0).  Final PSNR (mean of the last 50 steps) within 0.1 dB; both improve."""
+    from ideal_nerf_b200.train import TrainStep
+    b = O.synthetic_train_batch(0)
+    rays, bc = b["rays"].to(DEV), b["bc_rgb"].to(DEV)
+    aud, expr = b["aud"].to(DEV), b["expr"].to(DEV)
+    def network(seeds, mode):
+        args = M.default_args(dim_aud=64, dim_expr=76, perturb=0., mlp_mode=mode, lrate=3e-4)
+        net = M.Network(450, 450, 1200., O.NEAR, O.FAR, 8192, None, 64, 128, args=args)
+        for fn, seed in zip((net.face_nerf_coarse, net.face_nerf_fine), seeds):
+            fn.load_state_dict(O.normalise_density(O.init_face_nerf(seed), b["rays"], b["aud"], b["expr"], b["latent"]))
+        return net.to(DEV)
+
+    with torch.no_grad():
+        target = network((41, 42), "fp32").eval().render_rays(rays, bc, aud, None, b["latent"].to(DEV), expr, perturb=0.)["rgb_map"]
+    curves = {}
+    for mode in ("fp32", "bf16"):
+        net = network((43, 44), mode).train()
+        lat = torch.ones(4, 32, device=DEV)
+        step = TrainStep(net, lat, net.args)
+        losses = []
+        for i in range(500):
+            losses.append(step(rays, bc, target, aud, expr, 1, perturb=0.)["img_loss"])
+        curves[mode] = -10. * torch.log10(torch.stack(losses)).cpu()
+    p32, p16 = curves["fp32"], curves["bf16"]
+    print(f"PSNR step 0: fp32 {float(p32[0]):.3f} bf16 {float(p16[0]):.3f}; last-50 mean: fp32 {float(p32[-50:].mean()):.3f} "
+          f"bf16 {float(p16[-50:].mean()):.3f}; max |delta| over the run {float((p32 - p16).abs().max()):.3f} dB")
+    assert float(p32[-50:].mean()) > float(p32[0]) + 1.0 and float(p16[-50:].mean()) > float(p16[0]) + 1.0
+    assert abs(float(p32[-50:].mean()) - float(p16[-50:].mean())) <= 0.1

@@ -178,7 +178,7 @@ def test_flat_params_adam_equals_per_parameter_adam():
 
 
 def test_bench_reference_arm_prints_one_json_line():
-    """bench.py --impl reference (the oracle port on the host cores) honours the driver's contract without a GPU: exactly one stdout
+    """bench.py --impl reference (the reference's own renderer from oracle/_ref on the host cores; the oracle port when absent) honours the driver's contract without a GPU: exactly one stdout
     line, the metric / unit / config of the product arm, impl = reference, a cpu_baseline and an e2e object of its own."""
     import json
     import os
@@ -193,5 +193,96 @@ def test_bench_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "rays/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["metric"].startswith("rays/sec render") and "workload" in d["config"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    from oracle import ref_import
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_import.available() else "port")     # oracle/_ref (or /root/reference) present?
+    assert d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def _reference_head():
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("neither /root/reference nor oracle/_ref is present")
+    return ref_import.import_head(force_cpu=True)
+
+
+def test_head_tar_interchange_with_reference_adam(M, tmp_path):
+    """head.tar both ways (audio_exp_nerf.py:516-525 resume, :584-591 save) against the UNMODIFIED reference classes: a checkpoint written
+    by the reference's Network + per-parameter torch.optim.Adam loads into a live train.TrainStep with strict keys, IN PLACE (latent codes
+    and weights stay views of the flat Adam buffer -- ADVICE r1), the next update equals the reference's next update bit for bit, and the
+    file TrainStep.save() writes resumes the reference's own optimiser the same way."""
+    from ideal_nerf_b200.train import TrainStep
+    head = _reference_head()
+    torch.manual_seed(0)
+
+    def ref_setup():
+        net = head.Network(450, 450, 1200., 0.57, 1.17, 8192, None, 64, 128)
+        lat = torch.ones(5, 32)
+        lat.requires_grad = True
+        tp = list(net.parameters()) + [lat]                                   # :487-489
+        return net, lat, tp, torch.optim.Adam(params=tp, lr=3e-4, betas=(0.9, 0.999))
+
+    ref, lat_ref, tp, opt_ref = ref_setup()
+    ref.apply(head.init_weights)
+    g = torch.Generator().manual_seed(1)
+
+    def fake_grads(params_list):
+        gg = torch.Generator().manual_seed(int(torch.randint(1 << 30, (1,), generator=g)))
+        grads = [torch.randn(p.shape, generator=gg) * 1e-2 for p in tp]
+        for params in params_list:
+            for i, (p, gr) in enumerate(zip(params, grads)):
+                p.grad = None if 0 <= i - (len(tp) - 3) < 2 else gr.clone()     # ds_aud_net.* never receives a gradient in the reference
+    fake_grads([tp]); opt_ref.step()
+    fake_grads([tp]); opt_ref.step()
+    for gr in opt_ref.param_groups:
+        gr["lr"] = 2.9e-4
+    p1 = str(tmp_path / "head.tar")
+    torch.save({"global_step": 7, "model_state_dict": ref.state_dict(), "optimizer": opt_ref.state_dict(), "latent_codes": lat_ref.data}, p1)
+
+    ours = M.Network(450, 450, 1200., 0.57, 1.17, 8192, None, 64, 128)
+    lat = torch.zeros(5, 32)
+    ts = TrainStep(ours, lat, ours.args)
+    assert ts.load(p1) == 7 and ts.global_step == 7
+    assert ts.optimizer.param_groups[0]["lr"] == 2.9e-4
+    flat = ts.flat.flat
+    for p in ts.flat.params:                                                   # still views of the flat buffer after the load
+        assert flat.data_ptr() <= p.data_ptr() < flat.data_ptr() + flat.numel() * 4
+    assert list(ref.state_dict()) == list(ours.state_dict())
+    assert all(torch.equal(a, b) for a, b in zip(ref.state_dict().values(), ours.state_dict().values()))
+    assert torch.equal(lat.data, lat_ref.data)
+    before = lat.detach().clone()
+    fake_grads([tp, ts.flat.params])
+    opt_ref.step()
+    ts.flat.gather_grads(); ts.optimizer.step()
+    assert not torch.equal(lat.detach(), before), "latent codes must keep training after a resume"
+    assert all(torch.equal(p, q) for p, q in zip(tp, ts.flat.params)), "resumed update differs from the reference's"
+    # ... and back: the reference's resume code on a file written by TrainStep.save()
+    p2 = str(tmp_path / "head2.tar")
+    ts.global_step = 8
+    ts.save(p2)
+    ck = torch.load(p2, weights_only=False)
+    assert set(ck) == {"global_step", "model_state_dict", "optimizer", "latent_codes"}
+    ref2, lat2, tp2, opt2 = ref_setup()
+    ref2.load_state_dict(ck["model_state_dict"])                                # :521
+    lat2.data = ck["latent_codes"]                                              # :522
+    opt2.load_state_dict(ck["optimizer"])                                       # :524
+    fake_grads([tp, tp2])
+    opt_ref.step(); opt2.step()
+    assert all(torch.equal(p, q) for p, q in zip(tp, tp2))
+
+
+def test_load_head_checkpoint_copies_latents_in_place(M, tmp_path):
+    """load_head_checkpoint must not rebind latent_codes.data (TrainStep re-homes it as a view of the flat Adam buffer)."""
+    from ideal_nerf_b200 import checkpoint as ck
+    from ideal_nerf_b200.train import TrainStep
+    net = M.Network(450, 450, 1200., 0.57, 1.17, 8192, None, 64, 128)
+    lat = torch.ones(3, 32)
+    ts = TrainStep(net, lat, net.args)
+    p = str(tmp_path / "h.tar")
+    ck.save_head_checkpoint(p, net, None, torch.full((3, 32), 2.0), 5)
+    ptr = lat.data_ptr()
+    assert ck.load_head_checkpoint(p, net, None, lat) == 5
+    assert lat.data_ptr() == ptr and float(lat.detach().mean()) == 2.0
+    with pytest.raises(ValueError, match="TrainStep.load"):
+        ts.save(p)
+        ck.load_head_checkpoint(p, net, torch.optim.Adam([ts.flat.flat]), lat)

@@ -23,10 +23,17 @@ def _worker(rank, world, port, n_rays, q):
     full = torch.arange(n_rays * 3, dtype=torch.float32).reshape(n_rays, 3)     # the "rendered image"
     fr = FrameRenderer(network=None, rank=rank, world=world)
     out = fr.gather_image(full[lo:hi].clone(), n_rays)
+    ok = bool(torch.equal(out, full))                     # all-gather: every rank holds the image
+    # asynchronous, double-buffered form used by render_video: three frames in flight order, each consumed one frame late
+    hs = [fr.gather_image((full[lo:hi] + k).clone(), n_rays, async_op=True) for k in range(2)]
+    for k in range(2, 5):
+        ok = ok and bool(torch.equal(hs[k - 2].wait(), full + (k - 2)))
+        hs.append(fr.gather_image((full[lo:hi] + k).clone(), n_rays, async_op=True))
+    ok = ok and bool(torch.equal(hs[3].wait(), full + 3)) and bool(torch.equal(hs[4].wait(), full + 4))
     if rank == 0:
-        q.put((tuple(out.shape), bool(torch.equal(out, full))))
+        q.put((tuple(out.shape), ok))
     else:
-        assert out is None
+        assert ok
     # max-over-ranks timing reduction used by bench.py
     t = torch.tensor([float(rank + 1)], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -206,3 +206,17 @@ def test_dense_preset_rounding_floor(golden):
     print(f"reference fp32-vs-fp64 MLP on 256 dense-preset rays: rgb {d_rgb:.2e}, last_weight {d_lw:.2e}, rgb0 {d_rgb0:.2e}")
     assert d_rgb0 < 5e-6                     # the coarse pass is quiet ...
     assert 1e-5 < d_rgb < 1e-3 and 1e-5 < d_lw < 2e-3      # ... the fine pass amplifies rounding by 2-3 orders of magnitude
+
+
+def test_philox_restatement_known_answers():
+    """oracle/philox_ref.py against the Random123 known-answer vectors of philox4x32-10 (kat_vectors: counter, key -> output)."""
+    from oracle import philox_ref as P
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for c, k, want in kats:
+        got = tuple(int(x) for x in P.philox4x32_10(*c, *k))
+        assert got == want, (c, k, [hex(g) for g in got])
+    u = P.draws_u01(1234, 5, 1, 4097)
+    assert u.dtype.name == "float32" and u.shape == (4097,) and float(u.min()) >= 0.0 and float(u.max()) < 1.0
+    assert abs(float(u.mean()) - 0.5) < 0.02
