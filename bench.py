@@ -163,14 +163,14 @@ def reference_gpu_rays_per_s():
     dev = torch.device("cuda", 0)
     if kind == "reference":
         torch.set_default_tensor_type('torch.cuda.FloatTensor')
-        head = ref_import.import_head(perturb=0.0)
+        head = ref_import.import_head(perturb=1.0)
         net = head.Network(H, W, 1200., O.NEAR, O.FAR, 8192, None, S1, S_IMP)
         net.face_nerf_coarse.load_state_dict(c)
         net.face_nerf_fine.load_state_dict(f)
         net = net.to(dev)
         to = lambda t: t.to(dev)
         rays, bc, aud, expr, lat = to(fr["rays"]), to(fr["bc_rgb"]), to(fr["aud"]), to(fr["expr"]), to(fr["latent"])
-        frame = lambda: net.batchify_rays(rays, bc, aud, None, lat, expr, chunk=8192, perturb=0.)
+        frame = lambda: net.batchify_rays(rays, bc, aud, None, lat, expr, chunk=8192)       # perturb = args.perturb, captured at import (:298)
     else:
         to = lambda t: t.to(dev)
         c, f = {k: to(v) for k, v in c.items()}, {k: to(v) for k, v in f.items()}
@@ -272,15 +272,18 @@ def composite_standalone(M, dev, n_rays, reps=20):
     return tot_bytes, tot_ms
 
 
-def train_step_bench(M, dev, steps, mode="bf16", rank=0, world=1):
+def train_step_bench(M, dev, steps, mode="bf16", rank=0, world=1, cuda_graph=False):
     """BASELINE.json config 3: N_rand=3072 rays (64+128 samples), loss of audio_exp_nerf.py:540-548, backward through
-    compositing + both FaceNeRFs, Adam(lr=3e-4) step.  mode: bf16 = tcgen05 forward-with-save + chain + dW kernels; fp32 = FFMA.
+    compositing + both FaceNeRFs + AudioNet / AudioAttNet (the audio code is computed from an 8-frame DeepSpeech window inside the step,
+    :241-266), Adam(lr=3e-4) step and learning-rate schedule -- train.TrainStep, the repo's public training call.
+    mode: bf16 = tcgen05 forward-with-save + chain + dW kernels; fp32 = FFMA.  cuda_graph: the whole iteration as one graph launch.
     world > 1: data parallel, weak scaling -- every rank takes its own 3072 rays through identical weights, one NCCL all-reduce of the
     flat gradient (train.FlatParams.gather_grads, the reference's nn.DataParallel backward) before the optimiser step; time = max over ranks."""
     import torch.distributed as dist
     from ideal_nerf_b200 import synthetic as S, ops
+    from ideal_nerf_b200 import train as T
     cam, fr = S.camera(), S.frame_inputs(0)
-    a = M.default_args(dim_aud=64, dim_expr=76, perturb=1.0, mlp_mode=mode, N_samples=S1, N_importance=S_IMP)
+    a = M.default_args(dim_aud=64, dim_expr=76, perturb=1.0, mlp_mode=mode, N_samples=S1, N_importance=S_IMP, lrate=3e-4, nosmo_iters=0)
     net = M.Network(H, W, cam["focal"], S.NEAR, S.FAR, 8192, None, S1, S_IMP, args=a)
     torch.manual_seed(4321)
     net.apply(M.init_weights)
@@ -289,63 +292,62 @@ def train_step_bench(M, dev, steps, mode="bf16", rank=0, world=1):
     idx = torch.randperm(N_RAYS, generator=g)[:3072].to(dev)
     rays = ops.get_rays_packed(H, W, cam["focal"], cam["c2w"].to(dev), S.NEAR, S.FAR)[idx].contiguous()
     bc, tgt = fr["bc_rgb"].to(dev)[idx].contiguous(), torch.rand(3072, 3, generator=g).to(dev)
-    aud, expr = fr["aud"].to(dev), fr["expr"].to(dev)
-    lat = torch.ones(32, device=dev, requires_grad=True)
-    from ideal_nerf_b200 import train as T
-    params = list(net.parameters()) + [lat]
-    flat = T.FlatParams(params)                               # train.TrainStep's optimiser set-up: every parameter a view of one buffer
-    opt = torch.optim.Adam([flat.flat], lr=3e-4, betas=(0.9, 0.999), fused=True)
+    expr = fr["expr"].to(dev)
+    auds = torch.randn(40, 16, 29, generator=torch.Generator().manual_seed(6)).to(dev)       # synthetic DeepSpeech windows, 40 frames
+    lat = torch.ones(40, 32, device=dev)
+    ts = T.TrainStep(net, lat, a, world=world, cuda_graph=cuda_graph)
+    win = net.audio_window(auds, 17, 40)
 
     def step():
-        for p in params:
-            p.grad = None
-        r = net.render_rays(rays, bc, aud, None, lat, expr)
-        loss = T.head_loss(r, tgt, lat, 0.0005)[0]            # mse(rgb) + mse(rgb0) + 10 * lc_weight * ||latent||  (:540-548)
-        loss.backward()
-        flat.gather_grads(world)                              # + the gradient all-reduce when world > 1
-        opt.step()
-        return loss
+        return ts(rays, bc, tgt, None, expr, 17, aud_window=win)
 
-    for _ in range(2):
+    for _ in range(3):
         step()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0 = time.perf_counter()
     e0.record()
     for _ in range(steps):
-        loss = step()
+        out = step()
     e1.record()
+    host_ms = (time.perf_counter() - h0) * 1e3 / steps            # host time to ENQUEUE a step (no synchronisation inside)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    # per-kernel breakdown in a second pass: an event pair around each of the 17 launches of a 4.5 ms step would cost the step ~4 %
-    ops.LAUNCHES["count"] = 0
-    with ops.kernel_timing() as kt:
-        for _ in range(steps):
-            step()
-        torch.cuda.synchronize()
     ms = float(t.item())
-    kms = {k: v[1] / steps for k, v in kt.summary().items()}
-    out = {"rays_per_s": 3072 * world / (ms * 1e-3), "ms_per_step": ms, "n_rand": 3072 * world, "n_gpus": world, "mlp_mode": mode, "optimizer": "Adam lr=3e-4",
-           "loss": float(loss.detach()), "gpu_launches_per_step": ops.LAUNCHES["count"] / steps,
-           "kernels_ms_per_step": {k: round(v, 3) for k, v in kms.items()}}
-    if mode == "bf16":
-        # The three training kernels exchange their operands through HBM, so HBM bounds them.  Algorithmic bytes per
-        # 128-point tile: forward writes 40 activation images (16 KB) + 76 mask words x 128 rows; the chain reads the masks and writes 39
-        # delta images; dW reads every activation and delta image once.
-        tiles = 3072 * (S1 + S1 + S_IMP) // 128
-        per_tile = (40 + 39 + 79) * 16384 + 2 * 76 * 512
-        t_k = (kms.get("inerf_mlp_fwd_train", 0.0) + kms.get("inerf_mlp_bwd", 0.0)) * 1e-3
-        pk, pk_kind = peaks()
-        if t_k > 0:
-            ach = tiles * per_tile / t_k / 1e9
-            out["roofline"] = {"bound": "hbm", "kernels": "inerf_mlp_fwd_train + inerf_mlp_bwd (chain + dW)", "achieved": ach, "peak": pk["hbm_gbs"],
-                               "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "bytes_per_step": tiles * per_tile, "peak_kind": f"HBM copy, {pk_kind}"}
-    return out
+    res = {"rays_per_s": 3072 * world / (ms * 1e-3), "ms_per_step": ms, "host_ms_per_step": host_ms, "n_rand": 3072 * world, "n_gpus": world,
+           "mlp_mode": mode, "cuda_graph": bool(cuda_graph), "optimizer": "Adam lr=3e-4 (one flat tensor), lr schedule of :554-558",
+           "trains": "face_nerf_coarse, face_nerf_fine, aud_net, aud_att_net, latent_codes[index]", "loss": float(out["loss"])}
+    if not cuda_graph:
+        # per-kernel breakdown in a second pass: an event pair around each launch of a ~4 ms step would cost the step ~4 %
+        ops.LAUNCHES["count"] = 0
+        with ops.kernel_timing() as kt:
+            for _ in range(steps):
+                step()
+            torch.cuda.synchronize()
+        kms = {k: v[1] / steps for k, v in kt.summary().items()}
+        res["gpu_launches_per_step"] = ops.LAUNCHES["count"] / steps
+        res["kernels_ms_per_step"] = {k: round(v, 3) for k, v in kms.items()}
+        if mode == "bf16":
+            # The three training kernels exchange their operands through HBM, so HBM bounds them.  Algorithmic bytes per
+            # 128-point tile: forward writes 40 activation images (16 KB) + 76 mask words x 128 rows; the chain reads the masks and writes
+            # 39 delta images; dW reads every activation and delta image once.
+            tiles = 3072 * (S1 + S1 + S_IMP) // 128
+            per_tile = (40 + 39 + 79) * 16384 + 2 * 76 * 512
+            t_k = (kms.get("inerf_mlp_fwd_train", 0.0) + kms.get("inerf_mlp_bwd", 0.0)) * 1e-3
+            pk, pk_kind = peaks()
+            if t_k > 0:
+                ach = tiles * per_tile / t_k / 1e9
+                res["roofline"] = {"bound": "hbm", "kernels": "inerf_mlp_fwd_train + inerf_mlp_bwd (chain + dW)", "achieved": ach, "peak": pk["hbm_gbs"],
+                                   "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "bytes_per_step": tiles * per_tile, "peak_kind": f"HBM copy, {pk_kind}"}
+            flops = 3072 * (S1 + S1 + S_IMP) * 3_292_416           # fwd + bwd, 1 646 208 MAC per point
+            res["tensor_frac_of_sustained"] = flops / (ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]
+    return res
 
 
 def sampling_standalone(M, dev, n_rays, reps=20):
@@ -578,6 +580,8 @@ def run_ours(args):
             line["config5_video"] = video
         if train_bf16 is not None:
             line["train_step"] = train_bf16
+            if world == 1:
+                line["train_step_graph"] = train_step_bench(M, dev, 20, "bf16", cuda_graph=True)
         if world == 1 and not args.no_extra:
             line.update(extra_single_gpu(M, net, dev, res, args))
         if world == 1 and not args.no_train:

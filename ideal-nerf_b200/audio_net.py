@@ -1,8 +1,9 @@
 """Host-side mirror of models/audio_net.py: AudioNet and AudioAttNet with the reference's constructor arguments and state_dict keys
 (so `aud_net.*` / `aud_att_net.*` of a head.tar load unchanged); forward runs in the CUDA kernels of csrc/audio_net.cu.
 
-Inference only: the kernels have no backward.  Training the conditioning nets stays with the reference's PyTorch modules (they are
-0.02 % of a training step); calling these modules with autograd recording on their parameters raises."""
+Training: both modules are torch.autograd.Functions over the forward kernels and the backward kernels (inerf_audio_net_bwd,
+inerf_audio_att_bwd), so the audio code that conditions FaceNeRF carries gradients back into these weights exactly as in the reference,
+whose Adam optimises network.parameters() -- AudioNet and AudioAttNet included (audio_exp_nerf.py:263-266, :493)."""
 import ctypes
 
 import torch
@@ -11,23 +12,77 @@ import torch.nn as nn
 from . import _lib, ops
 
 
-def _params12(mods):
-    arr = (ctypes.c_void_p * 12)()
-    keep = []
-    for i, m in enumerate(mods):
-        for j, p in enumerate((m.weight, m.bias)):
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def _f32(ps):
+    return [p if (p.dtype == torch.float32 and p.is_contiguous()) else p.float().contiguous() for p in ps]
+
+
+class _AudioNetFn(torch.autograd.Function):
+    """AudioNet.forward as one kernel; backward = inerf_audio_net_bwd (forward recomputed in shared memory, no dx: the DeepSpeech
+    features are data)."""
+
+    @staticmethod
+    def forward(ctx, x, dim_aud, *params):
+        ps = _f32([p.detach() for p in params])
+        n = x.shape[0]
+        y = torch.empty((n, dim_aud), device=x.device)
+        with torch.cuda.device(x.device):
+            ops.call("inerf_audio_net_fwd", _lib.lib().inerf_audio_net_fwd, _ptr_array(ps), ops.ptr(x), n, dim_aud, ops.ptr(y), ops.stream())
+        ctx.save_for_backward(x, *ps)
+        ctx.dim_aud = dim_aud
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, *ps = ctx.saved_tensors
+        dy = ops.f32c(dy, "dy")
+        grads, _ = ops.zero_grads_like(ps)
+        with torch.cuda.device(x.device):
+            ops.call("inerf_audio_net_bwd", _lib.lib().inerf_audio_net_bwd, _ptr_array(ps), _ptr_array(grads), ops.ptr(x), ops.ptr(dy),
+                     x.shape[0], ctx.dim_aud, ops.stream())
+        return (None, None, *grads)
+
+
+class _AudioAttFn(torch.autograd.Function):
+    """AudioAttNet.forward as one kernel; backward = inerf_audio_att_bwd (returns dx for the AudioNet codes and the parameter gradients)."""
+
+    @staticmethod
+    def forward(ctx, x, seq_len, dim_att, *params):
+        ps = _f32([p.detach() for p in params])
+        y = torch.empty((x.shape[1],), device=x.device)
+        with torch.cuda.device(x.device):
+            ops.call("inerf_audio_att_fwd", _lib.lib().inerf_audio_att_fwd, _ptr_array(ps), ops.ptr(x), seq_len, x.shape[1], dim_att,
+                     ops.ptr(y), ops.stream())
+        ctx.save_for_backward(x, *ps)
+        ctx.meta = (seq_len, dim_att)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, *ps = ctx.saved_tensors
+        seq_len, dim_att = ctx.meta
+        dy = ops.f32c(dy, "dy")
+        grads, _ = ops.zero_grads_like(ps)
+        dx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            ops.call("inerf_audio_att_bwd", _lib.lib().inerf_audio_att_bwd, _ptr_array(ps), _ptr_array(grads), ops.ptr(x), ops.ptr(dy),
+                     seq_len, x.shape[1], dim_att, ops.ptr(dx), ops.stream())
+        return (dx, None, None, *grads)
+
+
+def _params_of(mods):
+    out = []
+    for m in mods:
+        for p in (m.weight, m.bias):
             ops._need_cuda(p, "parameter")
-            t = p.detach()
-            t = t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
-            keep.append(t)
-            arr[2 * i + j] = t.data_ptr()
-    return arr, keep
-
-
-def _no_grad_only(mod):
-    if torch.is_grad_enabled() and any(p.requires_grad for p in mod.parameters()):
-        raise NotImplementedError(f"{type(mod).__name__}: the CUDA kernel is forward-only; call it under torch.no_grad() / after "
-                                  "requires_grad_(False), or train this net with the reference module")
+            out.append(p)
+    return out
 
 
 class AudioNet(nn.Module):
@@ -44,17 +99,12 @@ class AudioNet(nn.Module):
         self.encoder_fc1 = nn.Sequential(nn.Linear(64, 64), nn.LeakyReLU(0.02, True), nn.Linear(64, dim_aud))
 
     def forward(self, x):
-        _no_grad_only(self)
         x = ops.f32c(x, "x")
         if x.dim() != 3 or x.shape[1:] != (16, 29):
             raise ValueError("AudioNet expects (n, 16, 29) DeepSpeech windows")
-        n = x.shape[0]
-        y = torch.empty((n, self.dim_aud), device=x.device)
-        arr, keep = _params12([self.encoder_conv[0], self.encoder_conv[2], self.encoder_conv[4], self.encoder_conv[6],
-                               self.encoder_fc1[0], self.encoder_fc1[2]])
-        with torch.cuda.device(x.device):
-            ops.call("inerf_audio_net_fwd", _lib.lib().inerf_audio_net_fwd, arr, ops.ptr(x), n, self.dim_aud, ops.ptr(y), ops.stream())
-        return y.squeeze()
+        ps = _params_of([self.encoder_conv[0], self.encoder_conv[2], self.encoder_conv[4], self.encoder_conv[6],
+                         self.encoder_fc1[0], self.encoder_fc1[2]])
+        return _AudioNetFn.apply(x, self.dim_aud, *ps).squeeze()
 
 
 class AudioAttNet(nn.Module):
@@ -70,14 +120,8 @@ class AudioAttNet(nn.Module):
         self.attentionNet = nn.Sequential(nn.Linear(seq_len, seq_len), nn.Softmax(dim=1))
 
     def forward(self, x):
-        _no_grad_only(self)
         x = ops.f32c(x, "x")
         if x.dim() != 2 or x.shape[0] != self.seq_len or x.shape[1] < self.dim_aud:
             raise ValueError("AudioAttNet expects (seq_len, dim_feat >= dim_aud) audio codes")
-        y = torch.empty((x.shape[1],), device=x.device)
         c = self.attentionConvNet
-        arr, keep = _params12([c[0], c[2], c[4], c[6], c[8], self.attentionNet[0]])
-        with torch.cuda.device(x.device):
-            ops.call("inerf_audio_att_fwd", _lib.lib().inerf_audio_att_fwd, arr, ops.ptr(x), self.seq_len, x.shape[1], self.dim_aud,
-                     ops.ptr(y), ops.stream())
-        return y
+        return _AudioAttFn.apply(x, self.seq_len, self.dim_aud, *_params_of([c[0], c[2], c[4], c[6], c[8], self.attentionNet[0]]))

@@ -756,8 +756,10 @@ struct PackArgs {
     uint8_t* blob;
 };
 
-__global__ void pack_kernel(const PackArgs* __restrict__ pa_ptr) {
-    const PackArgs& pa = *pa_ptr;
+// The argument table travels as a kernel parameter (2.4 KB, by value): nothing is copied from pageable host memory, so the launch can be
+// captured in a CUDA graph (train.TrainStep re-packs the weights after every optimiser step).
+static_assert(sizeof(PackArgs) <= 4000, "kernel parameter space");
+__global__ void pack_kernel(const __grid_constant__ PackArgs pa) {
     const PackStep st = pa.st[blockIdx.x];
     const float* W = pa.w[st.w_index];
     for (int i = threadIdx.x; i < st.rows * 64; i += blockDim.x) {
@@ -773,7 +775,7 @@ namespace inerf {
 
 int mlp_bf16_packed_bytes(const InerfNetDims* d, size_t* bytes) {
     Schedule S = build_schedule(d);
-    *bytes = (size_t)S.total_bytes + sizeof(PackArgs);        // tail: scratch for the pack kernel's argument table
+    *bytes = (size_t)S.total_bytes;
     return INERF_OK;
 }
 
@@ -784,11 +786,7 @@ int mlp_bf16_pack(const InerfNetDims* d, const float* const* params_host, void* 
     for (int i = 0; i < INERF_N_PARAMS; ++i) pa.w[i] = params_host[i];
     for (int i = 0; i < S.n_steps; ++i) pa.st[i] = S.pack[i];
     pa.blob = reinterpret_cast<uint8_t*>(packed);
-    PackArgs* dev_args = reinterpret_cast<PackArgs*>(pa.blob + S.total_bytes);
-    cudaError_t e = cudaMemcpyAsync(dev_args, &pa, sizeof(pa), cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) { set_error("inerf_mlp_pack: %s", cudaGetErrorString(e)); return (int)e; }
-    // pa lives on the stack: the copy above is from pageable memory and is staged before return
-    pack_kernel<<<S.n_steps, 256, 0, st>>>(dev_args);
+    pack_kernel<<<S.n_steps, 256, 0, st>>>(pa);
     return check_launch("inerf_mlp_pack");
 }
 

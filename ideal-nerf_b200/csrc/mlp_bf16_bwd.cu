@@ -423,8 +423,8 @@ struct BPackArgs {
     int n_steps;
 };
 
-__global__ void bwd_pack_kernel(const BPackArgs* __restrict__ pa_ptr) {
-    const BPackArgs& pa = *pa_ptr;
+static_assert(sizeof(BPackArgs) <= 4000, "kernel parameter space");
+__global__ void bwd_pack_kernel(const __grid_constant__ BPackArgs pa) {      // argument table by value: graph-capturable, no host copy
     if ((int)blockIdx.x < pa.n_steps) {
         const BPack st = pa.st[blockIdx.x];
         const float* W = pa.w[st.w_index];
@@ -454,7 +454,7 @@ namespace inerf {
 
 int mlp_bf16_bwd_packed_bytes(const InerfNetDims* d, size_t* bytes) {
     BSchedule S = build_bschedule(d);
-    *bytes = (size_t)S.stage_bytes + 2 * 4096 + sizeof(BPackArgs);
+    *bytes = (size_t)S.stage_bytes + 2 * 4096;
     return INERF_OK;
 }
 
@@ -467,10 +467,7 @@ int mlp_bf16_bwd_pack(const InerfNetDims* d, const float* const* params_host, vo
     pa.blob = reinterpret_cast<uint8_t*>(packed);
     pa.alpha_off = S.stage_bytes;
     pa.n_steps = S.n_steps;
-    BPackArgs* dev_args = reinterpret_cast<BPackArgs*>(pa.blob + S.stage_bytes + 2 * 4096);
-    cudaError_t e = cudaMemcpyAsync(dev_args, &pa, sizeof(pa), cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) { set_error("inerf_mlp_pack: %s", cudaGetErrorString(e)); return (int)e; }
-    bwd_pack_kernel<<<S.n_steps + 1, 256, 0, st>>>(dev_args);
+    bwd_pack_kernel<<<S.n_steps + 1, 256, 0, st>>>(pa);
     return check_launch("inerf_mlp_pack[bf16 bwd]");
 }
 

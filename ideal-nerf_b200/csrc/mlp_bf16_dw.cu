@@ -79,10 +79,11 @@ struct DwBars {
     int item;               // broadcast of the work counter
 };
 
-__global__ void __launch_bounds__(DW_THREADS, 1) mlp_bf16_dw_kernel(const DwArgs* __restrict__ ap) {
+static_assert(sizeof(DwArgs) <= 4000, "kernel parameter space");
+// The task table is a kernel parameter (by value): no copy from pageable host memory, so the launch is graph-capturable.
+__global__ void __launch_bounds__(DW_THREADS, 1) mlp_bf16_dw_kernel(const __grid_constant__ DwArgs a) {
     extern __shared__ __align__(1024) uint8_t sm[];
     if ((smem_u32(sm) & 1023u) != 0) __trap();
-    const DwArgs& a = *ap;
     DwBars* bars = reinterpret_cast<DwBars*>(sm + OFF_BARS);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) mlp_bf16_dw_kernel(const DwArgs
 
 namespace inerf {
 
-size_t mlp_bf16_dw_scratch_bytes() { return sizeof(DwArgs) + 16; }
+size_t mlp_bf16_dw_scratch_bytes() { return 16; }      // the work-item counter
 
 // delta_img / acts_img: [n_tiles][TRAIN_IMGS][16384].  grads_host: zero-initialised (or accumulating) gradient tensors, nn.Linear layout.
 // scratch: device, mlp_bf16_dw_scratch_bytes().
@@ -255,14 +256,12 @@ int mlp_bf16_dw_launch(const InerfNetDims* dims, float* const* grads_host, const
     if (chunks < 1) chunks = 1;
     d.tiles_per_chunk = (int)((n_tiles + chunks - 1) / chunks);
     d.n_chunks = (int)((n_tiles + d.tiles_per_chunk - 1) / d.tiles_per_chunk);
-    uint8_t* sc = reinterpret_cast<uint8_t*>(scratch);
-    d.counter = reinterpret_cast<int*>(sc + sizeof(DwArgs));
-    cudaError_t e = cudaMemcpyAsync(sc, &d, sizeof(d), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d.counter, 0, 16, st);
+    d.counter = reinterpret_cast<int*>(scratch);
+    cudaError_t e = cudaMemsetAsync(d.counter, 0, 16, st);
     if (e != cudaSuccess) { set_error("mlp_bf16_dw: %s", cudaGetErrorString(e)); return (int)e; }
     const int items = d.n_tasks * d.n_chunks;
     const int grid = items < num_sms() ? items : num_sms();
-    mlp_bf16_dw_kernel<<<grid, DW_THREADS, DW_SMEM, st>>>(reinterpret_cast<const DwArgs*>(sc));
+    mlp_bf16_dw_kernel<<<grid, DW_THREADS, DW_SMEM, st>>>(d);
     return check_launch("inerf_mlp_bwd[bf16 dW]");
 }
 

@@ -117,7 +117,7 @@ __device__ void gemm_layer(const float* __restrict__ W, int ldw, const Seg* segs
         const int n = 4 * tn + (j & 3) + 128 * (j >> 2);
         const float b = __ldg(bias + n);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[j][i] = fmaxf(acc[j][i] + b, 0.f);
+        for (int i = 0; i < 8; ++i) { const float v = acc[j][i] + b; acc[j][i] = v < 0.f ? 0.f : v; }      // F.relu: a NaN stays a NaN (fmaxf would swallow it)
         const int sw = (n >> 2) & 15;
         *reinterpret_cast<float4*>(out + n * TM + (((2 * tm) ^ sw) << 2)) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
         *reinterpret_cast<float4*>(out + n * TM + (((2 * tm + 1) ^ sw) << 2)) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);

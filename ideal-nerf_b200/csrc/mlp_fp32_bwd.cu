@@ -226,11 +226,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
-__global__ void __launch_bounds__(NTHREADS, 1) mlp_bwd_dw_kernel(const DwArgs* __restrict__ ap) {
+static_assert(sizeof(DwArgs) <= 4000, "kernel parameter space");
+__global__ void __launch_bounds__(NTHREADS, 1) mlp_bwd_dw_kernel(const __grid_constant__ DwArgs a) {      // table by value: graph-capturable
     extern __shared__ __align__(16) float sm[];
     float* As = sm;                        // 2 x [64 m][128 n]
     float* Bs = As + 2 * TM * 128;         // 2 x [64 m][128 k]
-    const DwArgs& a = *ap;
     const DwTile t = a.t[blockIdx.x];
     const int tid = threadIdx.x, tn = tid & 15, tk = tid >> 4;
     const long long per = (a.ntiles + a.split - 1) / a.split;
@@ -389,9 +389,8 @@ int mlp_fp32_bwd_launch(const InerfNetDims* dims, const float* const* params_hos
     d.n_out_tiles = nt;
     d.split = (int)((4 * (long long)num_sms() / nt) < 1 ? 1 : (4 * (long long)num_sms() / nt));
     if ((long long)d.split > ntiles) d.split = (int)ntiles;
-    cudaError_t e = cudaMemcpyAsync(dw_args_dev, &d, sizeof(d), cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) { set_error("inerf_mlp_bwd: %s", cudaGetErrorString(e)); return (int)e; }
-    mlp_bwd_dw_kernel<<<dim3(nt, d.split), NTHREADS, DW_SMEM, st>>>(reinterpret_cast<const DwArgs*>(dw_args_dev));
+    (void)dw_args_dev;
+    mlp_bwd_dw_kernel<<<dim3(nt, d.split), NTHREADS, DW_SMEM, st>>>(d);
     rc = check_launch("inerf_mlp_bwd[dW]");
     if (rc) return rc;
 

@@ -198,22 +198,25 @@ class Network(nn.Module):
     def audio_feature(self, auds, index, dataset_size, global_step=None):
         """The per-frame audio code of audio_exp_nerf.py:241-266: the smo_size-frame window around `index` (zero padded at the ends of
         the sequence) through AudioNet, then AudioAttNet; a single AudioNet call before `nosmo_iters`.  auds: (T, 16, 29) DeepSpeech
-        windows on the device.  Runs in the CUDA kernels of csrc/audio_net.cu (forward only)."""
+        windows on the device.  Runs in the CUDA kernels of csrc/audio_net.cu; differentiable in both nets' parameters when autograd is recording."""
         a = self.args
         if a.dim_aud <= 29:
             raise NotImplementedError("dim_aud <= 29 (DeepSpeechAudNet) is not a configuration the reference's configs use")
-        with torch.no_grad():
-            if global_step is None or global_step >= getattr(a, "nosmo_iters", 0):
-                half = int(getattr(a, "smo_size", 8) / 2)
-                left, right = index - half, index + half
-                pad_l, pad_r = max(0, -left), max(0, right - dataset_size)
-                win = auds[max(left, 0):min(right, dataset_size)]
-                if pad_l:
-                    win = torch.cat((torch.zeros_like(win)[:pad_l], win), 0)
-                if pad_r:
-                    win = torch.cat((win, torch.zeros_like(win)[:pad_r]), 0)
-                return self.aud_att_net(self.aud_net(win.contiguous()))
-            return self.aud_net(auds[index:index + 1].contiguous())
+        if global_step is None or global_step >= getattr(a, "nosmo_iters", 0):
+            return self.aud_att_net(self.aud_net(self.audio_window(auds, index, dataset_size)))
+        return self.aud_net(auds[index:index + 1].contiguous())
+
+    def audio_window(self, auds, index, dataset_size):
+        """The smo_size-frame window of DeepSpeech features around frame `index`, zero padded past either end (:243-262): (smo_size, 16, 29)."""
+        half = int(getattr(self.args, "smo_size", 8) / 2)
+        left, right = index - half, index + half
+        pad_l, pad_r = max(0, -left), max(0, right - dataset_size)
+        win = auds[max(left, 0):min(right, dataset_size)]
+        if pad_l:
+            win = torch.cat((torch.zeros_like(win)[:pad_l], win), 0)
+        if pad_r:
+            win = torch.cat((win, torch.zeros_like(win)[:pad_r]), 0)
+        return win.contiguous()
 
     def set_mlp_mode(self, mode):
         for m in self.modules():

@@ -77,11 +77,23 @@ class TrainStep:
     reference's per-parameter Adam state (params = list(network.parameters()) + [latent_codes], audio_exp_nerf.py:487-493) so the
     'optimizer' entry of head.tar moves both ways; `save()` / `load()` write and resume the reference's checkpoint (:516-525, :584-591)."""
 
-    def __init__(self, network, latent_codes, args, world=1, group=None):
+    def __init__(self, network, latent_codes, args, world=1, group=None, cuda_graph=False):
         self.net, self.latent_codes, self.args, self.world, self.group = network, latent_codes, args, world, group
         latent_codes.requires_grad_(True)
         self.flat = FlatParams(list(network.parameters()) + [latent_codes])
-        self.optimizer = torch.optim.Adam([self.flat.flat], lr=args.lrate, betas=(0.9, 0.999), fused=latent_codes.is_cuda)
+        self.cuda_graph = bool(cuda_graph)
+        self._static = None
+        if self.cuda_graph:
+            if not latent_codes.is_cuda:
+                raise RuntimeError("TrainStep(cuda_graph=True) needs CUDA tensors")
+            if world > 1:
+                raise NotImplementedError("cuda_graph=True is built for one process per model replica without a gradient all-reduce")
+            dev = latent_codes.device
+            self._lr_t = torch.tensor(float(args.lrate), device=dev)          # the learning rate and the step count live on the device
+            self._gs_t = torch.zeros((), device=dev)
+            self.optimizer = torch.optim.Adam([self.flat.flat], lr=self._lr_t, betas=(0.9, 0.999), fused=True, capturable=True)
+        else:
+            self.optimizer = torch.optim.Adam([self.flat.flat], lr=args.lrate, betas=(0.9, 0.999), fused=latent_codes.is_cuda)
         self.global_step = 0
 
     # -- checkpoint interchange with the reference's per-parameter Adam -----------------------------------------------------------
@@ -147,25 +159,95 @@ class TrainStep:
         else:
             for g in self.optimizer.param_groups:                          # the lr in force at step k is the one set after step k-1
                 g["lr"] = learning_rate(self.args, self.global_step - 1) if self.global_step > 0 else self.args.lrate
+        if self.cuda_graph:                                                # keep the device-resident schedule state the graph reads
+            if self._static is not None and self._static["graph"] is not None:
+                raise RuntimeError("TrainStep.load() after the CUDA graph was captured: load before the first graphed step")
+            for g in self.optimizer.param_groups:
+                self._lr_t.fill_(float(g["lr"]))
+                g["lr"] = self._lr_t
+            self._gs_t.fill_(float(self.global_step))
         for m in self.net.modules():
             if hasattr(m, "invalidate_packed"):
                 m.invalidate_packed()
         return self.global_step
 
-    def __call__(self, rays, bc_rgb, target, aud_feature, expr, index, perturb=None):
+    def __call__(self, rays, bc_rgb, target, aud_feature, expr, index, perturb=None, aud_window=None):
+        """aud_feature: the (dim_aud,) audio code (a constant, or a tensor with a graph into the conditioning nets); or pass
+        aud_window = the (smo_size, 16, 29) DeepSpeech window (Network.audio_window) and the code is computed -- and the two
+        conditioning nets are trained -- inside the step, as the reference's forward does (audio_exp_nerf.py:241-266)."""
+        perturb = self.args.perturb if perturb is None else perturb
+        if self.cuda_graph:
+            return self._graphed(rays, bc_rgb, target, aud_feature, expr, index, perturb, aud_window)
         a = self.args
         latent_code = self.latent_codes[index]
-        for p in self.flat.params:
-            p.grad = None
-        ret = self.net.render_rays(rays, bc_rgb, aud_feature, None, latent_code, expr, perturb=a.perturb if perturb is None else perturb)
-        loss, img_loss, latent_loss = head_loss(ret, target, latent_code, a.lc_weight)
-        loss.backward()
-        self.flat.gather_grads(self.world, self.group)
-        self.optimizer.step()
-        for m in (self.net.face_nerf_coarse, self.net.face_nerf_fine):      # fused Adam does not bump parameter versions
-            m.invalidate_packed()
+        if aud_window is not None:
+            aud_feature = self.net.aud_att_net(self.net.aud_net(aud_window))
+        loss, img_loss, latent_loss = self._body(rays, bc_rgb, target, aud_feature, expr, latent_code, perturb)
         lr = learning_rate(a, self.global_step)
         for g in self.optimizer.param_groups:
             g["lr"] = lr
         self.global_step += 1
         return {"loss": loss.detach(), "img_loss": img_loss.detach(), "latent_code_loss": latent_loss.detach(), "lr": lr}
+
+    def _body(self, rays, bc_rgb, target, aud_feature, expr, latent_code, perturb):
+        """Forward, loss, backward, gradient gather (+ all-reduce), Adam: everything between two learning-rate updates."""
+        for p in self.flat.params:
+            p.grad = None
+        ret = self.net.render_rays(rays, bc_rgb, aud_feature, None, latent_code, expr, perturb=perturb)
+        loss, img_loss, latent_loss = head_loss(ret, target, latent_code, self.args.lc_weight)
+        loss.backward()
+        self.flat.gather_grads(self.world, self.group)
+        self.optimizer.step()
+        for m in (self.net.face_nerf_coarse, self.net.face_nerf_fine):      # fused Adam does not bump parameter versions
+            m.invalidate_packed()
+        return loss, img_loss, latent_loss
+
+    # -- CUDA-graph mode (SURVEY.md 8f-2) ------------------------------------------------------------------------------------------
+    def _graphed(self, rays, bc_rgb, target, aud_feature, expr, index, perturb, aud_window):
+        """The whole iteration -- conditioning nets, both render passes, loss, backward, gradient gather, Adam, learning-rate schedule, RNG
+        offset -- as ONE cudaGraphLaunch.  Inputs are copied into static buffers; the latent-code row is selected on the device from a
+        one-element index tensor; the learning rate and Adam's step count live in device tensors updated inside the graph; the
+        stochastic draws come from the in-kernel Philox stream whose offset the graph advances.  The first call runs eagerly (it
+        initialises Adam's state and the kernels' per-device constants), the second call captures, every later call replays."""
+        dev = self.flat.flat.device
+        use_win = aud_window is not None
+        key = (tuple(rays.shape), tuple(bc_rgb.shape), use_win, float(perturb))
+        if self._static is None or self._static["key"] != key:
+            if self._static is not None:
+                raise RuntimeError(f"TrainStep(cuda_graph=True) was captured for {self._static['key']}, got {key}: batch shapes, the "
+                                   "aud_window / aud_feature choice and perturb are fixed per TrainStep")
+            aud_src = aud_window if use_win else aud_feature
+            self._static = {"key": key, "rays": torch.empty_like(rays), "bc": torch.empty_like(bc_rgb), "target": torch.empty_like(target),
+                            "aud": torch.empty_like(aud_src.detach()), "expr": torch.empty_like(expr),
+                            "idx": torch.zeros((1,), dtype=torch.int64, device=dev), "graph": None, "out": None, "calls": 0}
+        st = self._static
+        st["rays"].copy_(rays, non_blocking=True); st["bc"].copy_(bc_rgb, non_blocking=True); st["target"].copy_(target, non_blocking=True)
+        st["aud"].copy_((aud_window if use_win else aud_feature).detach(), non_blocking=True); st["expr"].copy_(expr, non_blocking=True)
+        if torch.is_tensor(index):
+            st["idx"].copy_(index.reshape(1), non_blocking=True)
+        else:
+            st["idx"].fill_(int(index))
+
+        def body():
+            latent_code = self.latent_codes.index_select(0, st["idx"]).squeeze(0)
+            aud = self.net.aud_att_net(self.net.aud_net(st["aud"])) if use_win else st["aud"]
+            loss, img_loss, latent_loss = self._body(st["rays"], st["bc"], st["target"], aud, st["expr"], latent_code, perturb)
+            # new_lrate = lrate * 0.1 ** (global_step / (lrate_decay * 1500)); global_step += 1      (:554-558), on the device
+            self._lr_t.copy_(self.args.lrate * torch.pow(0.1, self._gs_t / (self.args.lrate_decay * 1500)))
+            self._gs_t.add_(1.0)
+            return loss.detach(), img_loss.detach(), latent_loss.detach()
+
+        if st["calls"] == 0:
+            st["out"] = body()                                       # eager: lazy initialisations happen here
+        else:
+            if st["graph"] is None:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    st["out"] = body()
+                st["graph"] = g
+            st["graph"].replay()
+        st["calls"] += 1
+        self.global_step += 1
+        loss, img_loss, latent_loss = st["out"]
+        return {"loss": loss, "img_loss": img_loss, "latent_code_loss": latent_loss, "lr": self._lr_t}

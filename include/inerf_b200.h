@@ -271,7 +271,7 @@ int inerf_mlp_bwd_bf16(const InerfNetDims* dims, const float* const* params_host
                        const float* aud, const float* expr, const float* latent, const void* acts, const void* mask, void* deltas,
                        const float* d_raw, int64_t n_points, float* d_cond, void* scratch, void* stream);
 
-/* ---- per-frame conditioning nets (forward) -----------------------------------------------------------------------------------
+/* ---- per-frame conditioning nets -----------------------------------------------------------------------------------
  * AudioNet: DeepSpeech windows x (n, 16, 29) -> audio codes y (n, dim_aud).  Replaces models/audio_net.py:43-69 as called from
  * audio_exp_nerf.py:263,266.  params_host: 12 DEVICE pointers (host array) in state_dict order: encoder_conv.{0,2,4,6}.{weight,bias},
  * encoder_fc1.{0,2}.{weight,bias} (nn.Conv1d (out,in,3) / nn.Linear (out,in) layouts). */
@@ -280,6 +280,16 @@ int inerf_audio_net_fwd(const float* const* params_host, const float* x, int n, 
  * first dim_att (32) channels.  Replaces models/audio_net.py:8-36 (audio_exp_nerf.py:264).  params_host: 12 device pointers:
  * attentionConvNet.{0,2,4,6,8}.{weight,bias}, attentionNet.0.{weight,bias}. */
 int inerf_audio_att_fwd(const float* const* params_host, const float* x, int seq_len, int dim_feat, int dim_att, float* y, void* stream);
+
+/* Backward of the two conditioning nets: what autograd computes for models/audio_net.py inside the reference's loss.backward()
+ * (audio_exp_nerf.py:263-266 are in the graph; :493 optimises network.parameters(), these nets included).  The forward is recomputed
+ * in shared memory.  grads_host: 12 DEVICE pointers (host array) to gradient tensors in the parameters' layouts, ACCUMULATED into
+ * (zero them first).  inerf_audio_net_bwd: x (n,16,29), dy (n, dim_aud); the DeepSpeech features are data, so there is no dx.
+ * inerf_audio_att_bwd: x (8, dim_feat), dy (dim_feat) -> dx (8, dim_feat), overwritten. */
+int inerf_audio_net_bwd(const float* const* params_host, float* const* grads_host, const float* x, const float* dy, int n, int dim_aud,
+                        void* stream);
+int inerf_audio_att_bwd(const float* const* params_host, float* const* grads_host, const float* x, const float* dy, int seq_len,
+                        int dim_feat, int dim_att, float* dx, void* stream);
 
 /* After a failed inerf_mlp_fwd_trace (the trace build bounds every mbarrier wait to ~1 s and traps): the record
  * of the first waiter that timed out, {site code, block, thread, aux0, aux1, parity, 0, 0}; all zero otherwise.

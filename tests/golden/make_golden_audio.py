@@ -41,6 +41,29 @@ def main():
         out[f"att.x{d}"] = xw.numpy()
     for k, v in att.state_dict().items():
         out[f"att.{k}"] = v.numpy()
+    # ---- gradients: autograd of the unmodified modules (what loss.backward() computes for them, audio_exp_nerf.py:263-266,:549) ----
+    # chain of the training path: window (8,16,29) -> AudioNet -> (8,64) -> AudioAttNet -> (64,) -> <g_aud, .>
+    net = AudioNet(64, 16)
+    net.load_state_dict({k[len("an64."):]: torch.from_numpy(v) for k, v in out.items()
+                         if k.startswith("an64.") and k.split(".")[-1] in ("weight", "bias")})
+    x = torch.from_numpy(out["an64.x"])
+    g_aud = torch.randn(64, generator=g)
+    codes = net(x)
+    codes.retain_grad()
+    feat = att(codes)
+    (feat * g_aud).sum().backward()
+    out["grad.g_aud"], out["grad.feat"], out["grad.d_codes"] = g_aud.numpy(), feat.detach().numpy(), codes.grad.numpy()
+    for k, p in net.named_parameters():
+        out[f"grad.an64.{k}"] = p.grad.numpy()
+    for k, p in att.named_parameters():
+        out[f"grad.att.{k}"] = p.grad.numpy()
+    # the single-frame call before nosmo_iters (:266): AudioNet alone, n = 1
+    net.zero_grad()
+    g1 = torch.randn(64, generator=g)
+    (net(x[3:4]) * g1).sum().backward()
+    out["grad1.g"] = g1.numpy()
+    for k, p in net.named_parameters():
+        out[f"grad1.an64.{k}"] = p.grad.numpy()
     np.savez_compressed(os.path.join(HERE, "audio_nets.npz"), **out)
     print("wrote audio_nets.npz:", {k: v.shape for k, v in out.items() if k.endswith((".y", ".y1", "y64", "y76"))})
 
