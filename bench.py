@@ -635,6 +635,17 @@ def extra_single_gpu(M, net, dev, res, args):
                          "acc_max_abs": float((r_fast["acc_map"] - r32["acc_map"]).abs().max())}
         out["render_fp32"] = {"rays_per_s": N_RAYS / (ms32 * 1e-3), "ms_per_frame": ms32, "mlp_mode": "fp32 (FFMA, the <= 1e-3 max-abs mode)",
                               "frames": 1}
+        # the fp32-gate TENSOR-CORE mode (fp16 hi/lo operand pairs, 3 MMA passes): frame rate + agreement with the FFMA kernels
+        net.set_mlp_mode("fp16x2")
+        rx = render(0.)
+        msx = time_frames(lambda: render(1.0), 5)
+        net.set_mlp_mode(mode0)
+        pk, _ = peaks()
+        out["render_fp16x2"] = {"rays_per_s": N_RAYS / (msx * 1e-3), "ms_per_frame": msx,
+                                "mlp_mode": "fp16x2 (tcgen05, fp16 hi/lo operands, hi.hi + lo.hi + hi.lo, fp32 accumulate): the <= 1e-3 max-abs mode on tensor cores",
+                                "max_abs_vs_fp32_kernels": float((rx["rgb_map"] - r32["rgb_map"]).abs().max()),
+                                "tensor_frac_of_sustained": 3 * N_RAYS * (S1 + S1 + S_IMP) * FLOP_PER_POINT_FWD / (msx * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+                                "note": "tensor_frac counts the three MMA passes this mode issues per algorithmic product"}
         # config 4: head + torso composited frame with background blending (test_torso.py:516-523)
         tn, trays, bc, aud, pose, expr, lat = build_torso_network(args.mode, dev)
         step = lambda: tn(trays, trays, bc, aud, pose, expr, lat, perturb=1.0)

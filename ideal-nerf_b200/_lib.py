@@ -14,11 +14,11 @@ REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 SO_PATH = os.environ.get("INERF_SO") or os.path.join(PKG_DIR, "libinerf_b200.so")     # INERF_SO: profiling builds only
 SOURCES = ["api.cu", "rays.cu", "composite.cu", "sample_pdf.cu", "mlp_fp32.cu", "mlp_fp32_bwd.cu", "mlp_bf16.cu", "mlp_bf16_bwd.cu",
-           "mlp_bf16_dw.cu", "audio_net.cu"]
+           "mlp_bf16_dw.cu", "mlp_f16x2.cu", "audio_net.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--shared"]
 
-INERF_MLP_FP32, INERF_MLP_BF16, INERF_MLP_BF16_BWD = 0, 1, 2
+INERF_MLP_FP32, INERF_MLP_BF16, INERF_MLP_BF16_BWD, INERF_MLP_F16X2 = 0, 1, 2, 3
 INERF_PDF_EXACT_TORCH_CPU, INERF_PDF_FAST = 0, 1
 N_PARAMS = 26
 

@@ -16,6 +16,8 @@
 // network is 63->256, 4x(256->256), 319->256, 2x(256->256), {256->1, 283->128, 2x(128->128), 128->3}.
 #include <cuda_bf16.h>
 
+#include <cuda_fp16.h>
+
 #include "mlp_common.cuh"
 
 using namespace inerf;
@@ -297,6 +299,21 @@ __device__ __forceinline__ void write_bias_tile_row(uint8_t* tile, int r, float 
     *reinterpret_cast<uint4*>(p + 128) = make_uint4(0u, 0u, 0u, 0u);
 }
 
+// The same row for the fp32-gate tensor-core kernel (mlp_f16x2.cu): fp16, columns (hi, mid, lo, 0, ...) = the bias split in three fp16
+// numbers (exact to 2^-33 relative for |b| >= 2^-14); these tiles follow the bf16 ones in `cond`.
+__device__ __forceinline__ void write_bias_tile_row_f16x3(uint8_t* tile, int r, float b) {
+    const __half hi = __float2half_rn(b);
+    const float r1 = b - __half2float(hi);
+    const __half mid = __float2half_rn(r1);
+    const __half lo = __float2half_rn(r1 - __half2float(mid));
+    const uint32_t w0 = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(mid) << 16);
+    uint8_t* p = tile + (r >> 3) * 256 + (r & 7) * 16;
+    *reinterpret_cast<uint4*>(p) = make_uint4(w0, (uint32_t)__half_as_ushort(lo), 0u, 0u);
+    *reinterpret_cast<uint4*>(p + 128) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+constexpr int BIAS_TILE_BYTES = 16 * 4096 + 6 * 2048;      // per tile set: 8 layers x 2 halves x 4 KB + 3 layers x 2 halves x 2 KB
+
 __global__ void fold_cond_kernel(FoldArgs f) {
     __shared__ float c[1024];
     uint8_t* tiles = reinterpret_cast<uint8_t*>(f.cond + CondLayout{256, 128}.total());
@@ -324,6 +341,7 @@ __global__ void fold_cond_kernel(FoldArgs f) {
             if (lane == 0) {
                 f.cond[cl.pts(b) + n] = B[n] + s;
                 write_bias_tile_row(tiles + (2 * b + (n >> 7)) * 4096, n & 127, B[n] + s);
+                write_bias_tile_row_f16x3(tiles + BIAS_TILE_BYTES + (2 * b + (n >> 7)) * 4096, n & 127, B[n] + s);
             }
         }
     } else if (b < 11) {                          // views_linears.(b-8)
@@ -339,6 +357,7 @@ __global__ void fold_cond_kernel(FoldArgs f) {
             if (lane == 0) {
                 f.cond[cl.views(v) + n] = B[n] + s;
                 write_bias_tile_row(tiles + 65536 + (2 * v + (n >> 6)) * 2048, n & 63, B[n] + s);
+                write_bias_tile_row_f16x3(tiles + BIAS_TILE_BYTES + 65536 + (2 * v + (n >> 6)) * 2048, n & 63, B[n] + s);
             }
         }
     } else if (threadIdx.x < 4 && blockIdx.y == 0) {
@@ -390,8 +409,9 @@ extern "C" int inerf_mlp_cond_floats(const InerfNetDims* dims, size_t* n_floats)
     int rc = check_dims(dims);
     if (rc) return rc;
     if (!n_floats) return fail(INERF_E_ARG, "inerf_mlp_cond_floats: NULL");
-    // the folded fp32 biases, then the same biases as bf16 (hi, lo) operand tiles of the tensor-core kernel: 16 x 4 KB + 6 x 2 KB
-    *n_floats = (size_t)CondLayout{256, 128}.total() + (16 * 4096 + 6 * 2048) / sizeof(float);
+    // the folded fp32 biases, then the same biases as operand tiles of the tensor-core kernels (16 x 4 KB + 6 x 2 KB per set): bf16
+    // (hi, lo) for mlp_bf16.cu, fp16 (hi, mid, lo) for mlp_f16x2.cu
+    *n_floats = (size_t)CondLayout{256, 128}.total() + 2 * BIAS_TILE_BYTES / sizeof(float);
     return INERF_OK;
 }
 
@@ -421,6 +441,7 @@ extern "C" int inerf_mlp_packed_bytes(int mode, const InerfNetDims* dims, size_t
     if (mode == INERF_MLP_FP32) { *bytes = 0; return INERF_OK; }
     if (mode == INERF_MLP_BF16) return mlp_bf16_packed_bytes(dims, bytes);
     if (mode == INERF_MLP_BF16_BWD) return mlp_bf16_bwd_packed_bytes(dims, bytes);
+    if (mode == INERF_MLP_F16X2) return mlp_f16x2_packed_bytes(dims, bytes);
     return fail(INERF_E_UNSUPPORTED, "inerf_mlp_packed_bytes: unknown mode");
 }
 
@@ -436,6 +457,10 @@ extern "C" int inerf_mlp_pack(int mode, const InerfNetDims* dims, const float* c
     if (mode == INERF_MLP_BF16_BWD) {
         if (!params_host || !packed) return fail(INERF_E_ARG, "inerf_mlp_pack: NULL pointer");
         return mlp_bf16_bwd_pack(dims, params_host, packed, as_stream(stream));
+    }
+    if (mode == INERF_MLP_F16X2) {
+        if (!params_host || !packed) return fail(INERF_E_ARG, "inerf_mlp_pack: NULL pointer");
+        return mlp_f16x2_pack(dims, params_host, packed, as_stream(stream));
     }
     return fail(INERF_E_UNSUPPORTED, "inerf_mlp_pack: unknown mode");
 }
@@ -456,6 +481,10 @@ extern "C" int inerf_mlp_fwd(int mode, const InerfNetDims* dims, const float* co
     if (mode == INERF_MLP_BF16) {
         if (!packed) return fail(INERF_E_ARG, "inerf_mlp_fwd: bf16 mode needs packed weights");
         return mlp_bf16_launch(a, false, as_stream(stream));
+    }
+    if (mode == INERF_MLP_F16X2) {
+        if (!packed) return fail(INERF_E_ARG, "inerf_mlp_fwd: fp16x2 mode needs packed weights");
+        return mlp_f16x2_launch(a, as_stream(stream));
     }
     return fail(INERF_E_UNSUPPORTED, "inerf_mlp_fwd: unknown mode");
 }
@@ -547,6 +576,8 @@ extern "C" int inerf_mlp_fwd_embedded(int mode, const InerfNetDims* dims, const 
         if (!packed) return fail(INERF_E_ARG, "inerf_mlp_fwd_embedded: bf16 mode needs packed weights");
         return mlp_bf16_launch(a, true, as_stream(stream));
     }
+    if (mode == INERF_MLP_F16X2)
+        return fail(INERF_E_UNSUPPORTED, "fp16x2 mode is built for the fused (rays, z) entry; FaceNeRF.forward on embedded rows runs in fp32 mode");
     return fail(INERF_E_UNSUPPORTED, "inerf_mlp_fwd_embedded: unknown mode");
 }
 

@@ -11,7 +11,9 @@ import torch.nn as nn
 
 from . import _lib, ops
 
-MODES = {"fp32": _lib.INERF_MLP_FP32, "bf16": _lib.INERF_MLP_BF16}
+# "fp16x2": tensor cores at fp32-gate accuracy (fp16 hi/lo operand pairs, three MMA passes); inference kernel -- training in this mode
+# runs the fp32 kernels, like "fp32"
+MODES = {"fp32": _lib.INERF_MLP_FP32, "bf16": _lib.INERF_MLP_BF16, "fp16x2": _lib.INERF_MLP_F16X2}
 
 
 class FaceNeRF(nn.Module):
@@ -154,8 +156,9 @@ class _MlpFn(torch.autograd.Function):
             ctx.save_for_backward(acts, *[t for t in (aud_d, expr_d, lat_d) if t is not None], *pd)
             return out
         packed = net.packed_weights(params)
-        if embedded:
-            return ops.mlp_fwd_embedded(mode, net._dims, pd, packed, cond, a)
+        if embedded:                                         # FaceNeRF.forward on embedded rows: fp16x2 shares the fp32 kernel there
+            m = _lib.INERF_MLP_FP32 if mode == _lib.INERF_MLP_F16X2 else mode
+            return ops.mlp_fwd_embedded(m, net._dims, pd, packed, cond, a)
         return ops.mlp_fwd(mode, net._dims, pd, packed, cond, a, b)
 
     @staticmethod

@@ -42,7 +42,9 @@ enum {
 enum {
     INERF_MLP_FP32 = 0, /* fp32 FFMA, weights read in nn.Linear layout                         */
     INERF_MLP_BF16 = 1, /* bf16 operands, fp32 accumulate in TMEM, tcgen05.mma (packed weights) */
-    INERF_MLP_BF16_BWD = 2 /* inerf_mlp_packed_bytes / inerf_mlp_pack only: the TRANSPOSED stage images of the bf16 backward chain */
+    INERF_MLP_BF16_BWD = 2, /* inerf_mlp_packed_bytes / inerf_mlp_pack only: the TRANSPOSED stage images of the bf16 backward chain */
+    INERF_MLP_F16X2 = 3 /* fp32-gate tensor-core mode: every operand an fp16 (hi, lo) pair, three tcgen05 passes per product
+                           (hi.hi + lo.hi + hi.lo), fp32 accumulate in TMEM -- meets the <= 1e-3 max-abs gate (inference entry only) */
 };
 
 /* sample_pdf summation policies */

