@@ -29,6 +29,8 @@ struct MlpArgs {
     // memory -- TRAIN_IMGS 16 KB images [128 points][64 features] bf16, K-major, 128-byte swizzle -- and the ReLU masks
     uint8_t* save_img;                // [n_tiles][TRAIN_IMGS][16384]
     uint32_t* save_mask;              // [n_tiles][TRAIN_MASK_WORDS][128]: bit (31-j) of word w = pre-activation 32w+j of the row is >= 0
+    float tc_comp;                    // fp16x2 kernel, calibration runs only: uniform main-accumulator scale - 1 (< 0: use tc_ulps)
+    float tc_ulps[4];                 // fp16x2 kernel: main-accumulator compensation in ulps of 1.0 for {L0, L1-7, V0, V1-2}
 };
 
 // image index inside a tile: h0..h7 at 4l+kb, v0..v2 at 32+2v+kb, gamma(p) (63 cols) at 38, gamma(v) (27 cols) at 39; the backward

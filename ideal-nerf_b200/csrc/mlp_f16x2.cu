@@ -1,7 +1,12 @@
 // FaceNeRF MLP, fp32-GATE tensor-core mode ("fp16x2"): the fused tcgen05 kernel of mlp_bf16.cu with every operand carried as a
 // pair of fp16 numbers, x = x_hi + x_lo (22 significant bits), and every product formed by three tensor-core passes
 //     A.W  ~=  A_hi.W_hi + A_lo.W_hi + A_hi.W_lo            (the dropped A_lo.W_lo term is 2^-22 relative)
-// accumulated in fp32 in tensor memory.  This is the mode for north_star's "max-abs <= 1e-3 in fp32" gate at tensor-core speed:
+// accumulated in fp32 in tensor memory -- in TWO accumulators: the tensor core adds into its accumulator with truncation (round toward
+// zero), one biased rounding of the running sum per MMA, so the small correction passes (lo.hi, hi.lo: 2^-11 of the result) go to their
+// own accumulator, where the same truncation is 2^-11 smaller, and the main accumulator only sees the hi.hi passes (a third of the
+// roundings); the epilogue adds the two in fp32 with round-to-nearest (Ootomo & Yokota's error-corrected tensor-core GEMM uses the same
+// separation).  With one shared accumulator raw was 1e-5 of scale off the fp32 kernel, against 1.5e-6 for exact accumulation of the
+// same split operands (CPU emulation).  This is the mode for north_star's "max-abs <= 1e-3 in fp32" gate at tensor-core speed:
 // a single-pass bf16 / fp16 / tf32 kernel cannot meet it on the normalised-density preset, whose sigma ~ N(0, 8^2) amplifies operand
 // rounding ~100x (bf16 3.4e-2, fp16 = tf32 1.2e-2 max-abs on rgb_map, CPU emulation of the kernel's rounding points on the reference's
 // golden render), while the hi/lo split sits at the algorithm's own fp32 rounding floor (3-7e-4; profiles/r02_precision_modes.txt).
@@ -11,7 +16,8 @@
 //
 // Structure (differences from mlp_bf16.cu, whose barrier protocol is kept one to one):
 //   * a CTA iteration owns ONE 128-row slot; the shared-memory area that holds the second slot there holds the LOW halves here
-//     (activations 2 x 64 KB, gamma(p) 2 x 16 KB), so the memory map, the 3 x 16 KB weight ring and the TMEM columns are unchanged;
+//     (activations 2 x 64 KB, gamma(p) 2 x 16 KB), so the memory map and the 3 x 16 KB weight ring are unchanged; TMEM columns
+//     [0, 256) hold the main accumulator of the layer (both halves), [256, 512) the correction accumulator;
 //   * every weight K-block is streamed as two stages, W_hi then W_lo (the packed blob is twice as large: 2.2 MB / net, from L2);
 //     per K-block the issuer emits 12 MMAs (M = 128, N = 128 or 64, K = 16): 4 x A_hi.W_hi, 4 x A_lo.W_hi on the first stage,
 //     4 x A_hi.W_lo on the second -- three times the tensor work per point of the bf16 kernel;
@@ -25,6 +31,7 @@
 //     here), split into hi / lo like the activations; gamma(viewdir) as a per-ray fp32 bias vector, as in the bf16 kernel.
 // Every mbarrier wait is bounded (~2 s) and traps instead of hanging the GPU.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "mlp_common.cuh"
 #include "sm100_ptx.cuh"
@@ -120,6 +127,29 @@ __device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32
         : "memory");
 }
 
+// 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+constexpr uint32_t CORR_COL = 256;      // first TMEM column of the correction accumulator
+// Compensation of the tensor core's accumulation rounding.  tcgen05.mma adds into its fp32 accumulator with round-toward-zero: each of
+// the n MMAs that accumulate into the main accumulator of a layer (1 bias MMA + 4 per K-block: 5 for pts_linears.0, 17 for the 256-wide
+// layers and views_linears.0, 21 for the skip layer, 9 for views_linears.1-2) shrinks the running sum by half an ulp on average -- a
+// multiplicative bias of ~n x 1.8e-8 per layer that adds up coherently over the 11 layers (measured: raw sigma +7.7e-7 of scale off in
+// the mean, 3.5e-6 max, against 1.5e-6 max for the fp32 FFMA kernel; profiles/r02_f16x2_comp.txt).  The epilogue adds the two
+// accumulators as fma(main, 1 + comp, correction) -- the same instruction count as the plain add -- with comp = n x 2.9e-8 (the expected
+// shrink: n/3 ulps of the final sum, a random walk of partial sums) rounded to fp32 ulps of 1.0 (2^-23): 1 for L0, 4 for the 256-wide
+// layers, 2 for V0 / V1-2 (V0's theoretical 4 is indistinguishable in the sweep; the landscape is flat to 5 % around this point).  It
+// brings raw to 2.0e-6 max / 5e-7 rms of scale, against 1.5e-6 / 3.3e-7 for the FFMA kernel and 3.5e-6 / 1.0e-6 uncompensated.
+// INERF_F16X2_COMP (uniform comp) / INERF_F16X2_ULPS ("l0,trunk,v0,v12") re-run the calibration (tests/native/f16x2_comp_sweep.py).
+__host__ __device__ constexpr float tc_comp_ulps(int l) { return l == 0 ? 1.0f : (l < 8 ? 4.0f : 2.0f); }
 constexpr uint32_t HI_NOSWZ = (256u >> 4) | (1u << 14);
 __device__ __forceinline__ uint32_t desc_lo_noswz(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | ((128u >> 4) << 16); }
 
@@ -172,10 +202,10 @@ __device__ __forceinline__ void issue_layer(IssueCtx& c) {
                 }
             }
             if (L == 0 && h == 0 && i == 0) wait_b(&bars->pe_ready, c.iter_ctr & 1);
-            const uint32_t d = c.tmem_base + h * NH;
+            const uint32_t d = c.tmem_base + h * NH, dc = d + CORR_COL;      // main / correction accumulator
             const uint32_t a_hi = is_pe ? c.pe_lo : c.a_lo + i * (16384 >> 4);
             const uint32_t a_lo = is_pe ? c.pe_lo + (16384 >> 4) : c.a_lo + (65536 >> 4) + i * (16384 >> 4);
-            // ---- stage 1: W_hi -- A_hi.W_hi + A_lo.W_hi -------------------------------------------------------------------
+            // ---- stage 1: W_hi -- A_hi.W_hi -> main, A_lo.W_hi -> correction ------------------------------------------------
             wait_b(&bars->wfull[c.stage], c.wpar);
             if (i == 0) wait_b(&bars->bfull[c.bslot], c.bpar);
             tc_fence_after();
@@ -188,19 +218,19 @@ __device__ __forceinline__ void issue_layer(IssueCtx& c) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_lohi(d, a_hi + 2 * k, b + 2 * k, c.hi, IDESC, 1u);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_lohi(d, a_lo + 2 * k, b + 2 * k, c.hi, IDESC, 1u);
+                for (int k = 0; k < 4; ++k) umma_lohi(dc, a_lo + 2 * k, b + 2 * k, c.hi, IDESC, (i == 0 && k == 0) ? 0u : 1u);
                 umma_commit(&bars->wempty[c.stage]);
             }
             __syncwarp();
             if (i == 0) { c.bslot ^= 1; if (c.bslot == 0) c.bpar ^= 1; }
             if (++c.stage == NSTAGE) { c.stage = 0; c.wpar ^= 1; }
-            // ---- stage 2: W_lo -- A_hi.W_lo ---------------------------------------------------------------------------------
+            // ---- stage 2: W_lo -- A_hi.W_lo -> correction -------------------------------------------------------------------
             wait_b(&bars->wfull[c.stage], c.wpar);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t b = c.w_lo + c.stage * (STAGE_BYTES >> 4);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_lohi(d, a_hi + 2 * k, b + 2 * k, c.hi, IDESC, 1u);
+                for (int k = 0; k < 4; ++k) umma_lohi(dc, a_hi + 2 * k, b + 2 * k, c.hi, IDESC, 1u);
                 umma_commit(&bars->wempty[c.stage]);
                 const bool last = (i == CNT - 1);
                 if (h == 0 && last) umma_commit(&bars->cbar[0]);
@@ -215,14 +245,16 @@ __device__ __forceinline__ void issue_layer(IssueCtx& c) {
     ++c.layer_ctr;
 }
 
-// One 32-column chunk of an epilogue.  KIND 0: plain; 1: + alpha_linear partial (L7); 2: + per-ray view bias (V0); 3: + rgb_linear (V2)
+// Sixteen columns of an epilogue: main + correction accumulator (fp32, round to nearest), then
+// KIND 0: plain; 1: + alpha_linear partial (L7); 2: + per-ray view bias (V0); 3: + rgb_linear partial (V2); ReLU and hi / lo split
 template <int KIND>
-__device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], uint32_t* __restrict__ ph, uint32_t* __restrict__ pl,
-                                          const float* __restrict__ dsrc, const float* __restrict__ aw, const float* __restrict__ rw,
-                                          float& alpha, float& rgb0, float& rgb1, float& rgb2) {
+__device__ __forceinline__ void epi16(const uint32_t (&r)[16], const uint32_t (&rc)[16], uint32_t* __restrict__ ph, uint32_t* __restrict__ pl,
+                                      const float* __restrict__ dsrc, const float* __restrict__ aw, const float* __restrict__ rw,
+                                      float& alpha, float& rgb0, float& rgb1, float& rgb2, const float ms) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-        float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])};
+    for (int j = 0; j < 16; j += 4) {
+        float v[4] = {fmaf(__uint_as_float(r[j]), ms, __uint_as_float(rc[j])), fmaf(__uint_as_float(r[j + 1]), ms, __uint_as_float(rc[j + 1])),
+                      fmaf(__uint_as_float(r[j + 2]), ms, __uint_as_float(rc[j + 2])), fmaf(__uint_as_float(r[j + 3]), ms, __uint_as_float(rc[j + 3]))};
         if constexpr (KIND == 2) {
             const float4 d = *reinterpret_cast<const float4*>(dsrc + j);
             v[0] += d.x; v[1] += d.y; v[2] += d.z; v[3] += d.w;
@@ -278,7 +310,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_f16x2_kernel(MlpArgs a, int n
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(&bars->tmem_base, 256);
+        tmem_alloc(&bars->tmem_base, 512);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -357,6 +389,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_f16x2_kernel(MlpArgs a, int n
                 const int NH = (l < 8 ? 256 : 128) >> 1;
                 const int npg = NH >> 6;                       // chunks per group and half: 2 (N = 256) or 1 (N = 128)
                 const uint32_t par = layer_ctr & 1;
+                const float ms = a.tc_comp >= 0.f ? 1.0f + a.tc_comp : 1.0f + a.tc_ulps[l == 0 ? 0 : (l < 8 ? 1 : (l == 8 ? 2 : 3))] * 1.1920928955078125e-07f;
                 if (l == 8) wait_b(&bars->dirb_ready, iter_ctr & 1);
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
@@ -368,14 +401,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_f16x2_kernel(MlpArgs a, int n
                     for (int cc = 0; cc < 2; ++cc) {
                         if (cc < npg) {
                             const int f0 = h * NH + (grp * npg + cc) * 32;       // first output feature of the chunk
-                            uint32_t r[32];
-                            tmem_ld32(t_lane + f0, r);
-                            tmem_wait_ld();
-                            switch (l) {
-                                case 7: epi_chunk<1>(r, &ph[cc * 16], &pl[cc * 16], nullptr, s_aw + f0, nullptr, alpha, rgb0, rgb1, rgb2); break;
-                                case 8: epi_chunk<2>(r, &ph[cc * 16], &pl[cc * 16], s_dirb + ray_local * 128 + f0, nullptr, nullptr, alpha, rgb0, rgb1, rgb2); break;
-                                case 10: epi_chunk<3>(r, &ph[cc * 16], &pl[cc * 16], nullptr, nullptr, s_rw + f0, alpha, rgb0, rgb1, rgb2); break;
-                                default: epi_chunk<0>(r, &ph[cc * 16], &pl[cc * 16], nullptr, nullptr, nullptr, alpha, rgb0, rgb1, rgb2); break;
+#pragma unroll
+                            for (int q16 = 0; q16 < 2; ++q16) {
+                                const int f = f0 + q16 * 16;
+                                uint32_t r[16], rc[16];
+                                tmem_ld16(t_lane + f, r);
+                                tmem_ld16(t_lane + CORR_COL + f, rc);
+                                tmem_wait_ld();
+                                uint32_t* oh = &ph[cc * 16 + q16 * 8];
+                                uint32_t* ol = &pl[cc * 16 + q16 * 8];
+                                switch (l) {
+                                    case 7: epi16<1>(r, rc, oh, ol, nullptr, s_aw + f, nullptr, alpha, rgb0, rgb1, rgb2, ms); break;
+                                    case 8: epi16<2>(r, rc, oh, ol, s_dirb + ray_local * 128 + f, nullptr, nullptr, alpha, rgb0, rgb1, rgb2, ms); break;
+                                    case 10: epi16<3>(r, rc, oh, ol, nullptr, nullptr, s_rw + f, alpha, rgb0, rgb1, rgb2, ms); break;
+                                    default: epi16<0>(r, rc, oh, ol, nullptr, nullptr, nullptr, alpha, rgb0, rgb1, rgb2, ms); break;
+                                }
                             }
                         }
                     }
@@ -510,7 +550,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_f16x2_kernel(MlpArgs a, int n
     // ---- teardown ---------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 256);
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -616,7 +656,12 @@ int mlp_f16x2_launch(const MlpArgs& a, cudaStream_t st) {
     }
     const long long n_iter = (a.P + 127) / 128;
     const int grid = (int)(n_iter < (long long)num_sms() ? n_iter : (long long)num_sms());
-    mlp_f16x2_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(a, S.n_stages, (int)(a.P / a.s));
+    MlpArgs b = a;
+    b.tc_comp = -1.0f;                                                                // < 0: the per-layer table tc_comp_ulps
+    b.tc_ulps[0] = tc_comp_ulps(0); b.tc_ulps[1] = tc_comp_ulps(1); b.tc_ulps[2] = tc_comp_ulps(8); b.tc_ulps[3] = tc_comp_ulps(9);
+    if (const char* e = getenv("INERF_F16X2_COMP")) b.tc_comp = (float)atof(e);      // calibration sweeps (tests/native/f16x2_comp_sweep.py)
+    if (const char* e = getenv("INERF_F16X2_ULPS")) sscanf(e, "%f,%f,%f,%f", &b.tc_ulps[0], &b.tc_ulps[1], &b.tc_ulps[2], &b.tc_ulps[3]);
+    mlp_f16x2_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(b, S.n_stages, (int)(a.P / a.s));
     return check_launch("inerf_mlp_fwd[fp16x2]");
 }
 
