@@ -1,5 +1,5 @@
 import sys, numpy as np, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))))
 from oracle import render_oracle as O
 torch.set_num_threads(8)
 def f16(x): return x.to(torch.float16).to(x.dtype)

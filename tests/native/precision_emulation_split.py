@@ -1,8 +1,8 @@
 import sys, numpy as np, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))))
 from oracle import render_oracle as O
 torch.set_num_threads(8)
-g = dict(np.load('/root/repo/tests/golden/render_3072.npz'))
+g = dict(np.load(__import__('os').path.join(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))), 'golden', 'render_3072.npz')))
 def f16(x): return x.to(torch.float16).float()
 def split_rn(x):
     hi = f16(x); lo = f16(x - hi); return hi, lo

@@ -1062,16 +1062,17 @@ def test_sample_coarse_rng_bit_exact_vs_philox_oracle(M, lindisp):
     for the same (seed, offset): bit-exact, including a second call after inerf_rng_advance."""
     from oracle import philox_ref as P
     b = O.synthetic_train_batch(0)
-    n, s = 777, 64
+    n = 777
     rays = b["rays"][:n].to(DEV)
     st = torch.tensor([0x1234567 + (5 << 32), 40], dtype=torch.int64, device=DEV)
-    for k in range(2):
+    for k, s in enumerate((64, 64, 45)):           # s % 4 == 0: four draws of one Philox block per thread; otherwise one draw per thread
         z = M.ops.sample_coarse_rng(rays, s, st, lindisp, advance=True)
         u = torch.from_numpy(P.draws_u01(0x1234567 + (5 << 32), 40 + k, 1, n * s)).reshape(n, s)
         want = M.ops.sample_coarse(rays, s, u.to(DEV), lindisp)
         assert bits_equal(z, want), f"call {k}"
         assert bits_equal(want.cpu(), O.stratified_z(b["rays"][:n, 6:7], b["rays"][:n, 7:8], s, n, u, lindisp))
-    assert st.tolist() == [0x1234567 + (5 << 32), 42]
+    assert st.tolist() == [0x1234567 + (5 << 32), 43]
+    s = 64
     assert M.ops.sample_coarse_rng(rays[:0], s, st).shape == (0, s)
 
 
