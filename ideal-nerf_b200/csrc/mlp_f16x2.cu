@@ -278,7 +278,9 @@ __device__ __forceinline__ void epi16(const uint32_t (&r)[16], const uint32_t (&
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) mlp_f16x2_kernel(MlpArgs a, int n_stages, int n_rays) {
+// abl (profiling only, INERF_F16X2_ABL; results are garbage): bit 0 = the weight ring is filled once and never reloaded, bit 1 = the
+// epilogue keeps its barrier protocol but skips the TMEM loads / conversion / stores, bit 2 = the positional-encoding warps skip sincosf
+__global__ void __launch_bounds__(NTHREADS, 1) mlp_f16x2_kernel(MlpArgs a, int n_stages, int n_rays, int abl) {
     extern __shared__ __align__(1024) uint8_t sm[];
     if ((smem_u32(sm) & 1023u) != 0) __trap();
     Bars* bars = reinterpret_cast<Bars*>(sm + OFF_BAR);
@@ -339,6 +341,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_f16x2_kernel(MlpArgs a, int n
                     }
                     wait_b(&bars->wempty[stage], (round & 1) ^ 1);
                     const uint32_t bytes = (uint32_t)fs.n8 * 8u * 128u;
+                    if ((abl & 1) && g >= NSTAGE) { mbar_arrive(&bars->wfull[stage]); continue; }
                     mbar_arrive_expect_tx(&bars->wfull[stage], bytes);
                     bulk_g2s(sm + OFF_W + stage * STAGE_BYTES, blob + fs.offset, bytes, &bars->wfull[stage]);
                 }
@@ -399,7 +402,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_f16x2_kernel(MlpArgs a, int n
                     uint32_t ph[32], pl[32];
 #pragma unroll
                     for (int cc = 0; cc < 2; ++cc) {
-                        if (cc < npg) {
+                        if (cc < npg && !(abl & 2)) {
                             const int f0 = h * NH + (grp * npg + cc) * 32;       // first output feature of the chunk
 #pragma unroll
                             for (int q16 = 0; q16 < 2; ++q16) {
@@ -425,7 +428,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_f16x2_kernel(MlpArgs a, int n
                         __syncwarp();
 #pragma unroll
                         for (int cc = 0; cc < 2; ++cc) {
-                            if (cc < npg) {
+                            if (cc < npg && !(abl & 2)) {
                                 const int f0 = h * NH + (grp * npg + cc) * 32;
                                 uint8_t* kb = act + (f0 >> 6) * 16384 + row_off;
                                 const int ch0 = (f0 & 63) >> 3;
@@ -492,7 +495,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_f16x2_kernel(MlpArgs a, int n
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         float sn, cs;
-                        sincosf(v[c] * (float)(1 << f), &sn, &cs);
+                        if (abl & 4) { sn = v[c]; cs = zz; }
+                        else sincosf(v[c] * (float)(1 << f), &sn, &cs);
                         v[3 + 6 * f + c] = sn;
                         v[6 + 6 * f + c] = cs;
                     }
@@ -661,7 +665,9 @@ int mlp_f16x2_launch(const MlpArgs& a, cudaStream_t st) {
     b.tc_ulps[0] = tc_comp_ulps(0); b.tc_ulps[1] = tc_comp_ulps(1); b.tc_ulps[2] = tc_comp_ulps(8); b.tc_ulps[3] = tc_comp_ulps(9);
     if (const char* e = getenv("INERF_F16X2_COMP")) b.tc_comp = (float)atof(e);      // calibration sweeps (tests/native/f16x2_comp_sweep.py)
     if (const char* e = getenv("INERF_F16X2_ULPS")) sscanf(e, "%f,%f,%f,%f", &b.tc_ulps[0], &b.tc_ulps[1], &b.tc_ulps[2], &b.tc_ulps[3]);
-    mlp_f16x2_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(b, S.n_stages, (int)(a.P / a.s));
+    int abl = 0;
+    if (const char* e = getenv("INERF_F16X2_ABL")) abl = atoi(e);
+    mlp_f16x2_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(b, S.n_stages, (int)(a.P / a.s), abl);
     return check_launch("inerf_mlp_fwd[fp16x2]");
 }
 
