@@ -16,6 +16,14 @@
  *   - return 0 on success, a negative INERF_E_* on bad arguments, a positive cudaError_t when the
  *     CUDA runtime reports a launch error; inerf_last_error() gives the message (thread local);
  *   - re-entrant per (device, stream); no global mutable state besides the last-error string.
+ *
+ * Limits (every one is reported as INERF_E_UNSUPPORTED / INERF_E_SHAPE with a message, never silently worked around):
+ *   - FaceNeRF geometry: D = 8, W = 256, skips = [4], in_xyz = 63, in_views = 27, use_viewdirs (the configuration of every reference
+ *     script); conditioning dims are free (head 64 + 76 + 32, torso 106 + 0 + 0, ...);
+ *   - the tensor-core modes (INERF_MLP_BF16, INERF_MLP_F16X2) need s >= 43 samples per ray (a 128-row slot may touch at most four
+ *     rays) and exist for the fused (rays, z) entry inerf_mlp_fwd; inerf_mlp_fwd_embedded runs INERF_MLP_FP32 only;
+ *   - training entry points exist for INERF_MLP_FP32 and INERF_MLP_BF16 (INERF_MLP_F16X2 is an inference mode);
+ *   - sample_pdf: 2 <= n_bins <= 1024, n_imp <= 1024, the per-ray working set within 48 KB of shared memory; s <= 4096 elsewhere.
  */
 #ifndef INERF_B200_H
 #define INERF_B200_H
