@@ -94,6 +94,11 @@ struct Bars {
     uint32_t tmem_base;
 };
 
+// The MMA issuer's waits sit on the critical path of the tensor pipe (the bf16 kernel lost 3 % when its issuer got the bounded form):
+// the issuer polls with the plain try_wait loop; every wait it depends on is made by a warp that IS bounded, so a protocol error still
+// ends in a trap of that warp (and the launch failing), not in a hang.
+__device__ __forceinline__ void wait_i(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
+
 __device__ __forceinline__ void wait_b(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
@@ -195,19 +200,19 @@ __device__ __forceinline__ void issue_layer(IssueCtx& c) {
             const bool is_pe = (i == NKB);
             if (h == 0 && c.layer_ctr > 0) {
                 if (L == 0) {
-                    if (i == 0) { wait_b(&bars->ebar[0], par_prev); wait_b(&bars->ebar[1], par_prev); }
+                    if (i == 0) { wait_i(&bars->ebar[0], par_prev); wait_i(&bars->ebar[1], par_prev); }
                 } else if (!is_pe) {
-                    if (i == 0) wait_b(&bars->ebar[0], par_prev);
-                    if (i == KB_PER_HALF_PREV) wait_b(&bars->ebar[1], par_prev);
+                    if (i == 0) wait_i(&bars->ebar[0], par_prev);
+                    if (i == KB_PER_HALF_PREV) wait_i(&bars->ebar[1], par_prev);
                 }
             }
-            if (L == 0 && h == 0 && i == 0) wait_b(&bars->pe_ready, c.iter_ctr & 1);
+            if (L == 0 && h == 0 && i == 0) wait_i(&bars->pe_ready, c.iter_ctr & 1);
             const uint32_t d = c.tmem_base + h * NH, dc = d + CORR_COL;      // main / correction accumulator
             const uint32_t a_hi = is_pe ? c.pe_lo : c.a_lo + i * (16384 >> 4);
             const uint32_t a_lo = is_pe ? c.pe_lo + (16384 >> 4) : c.a_lo + (65536 >> 4) + i * (16384 >> 4);
             // ---- stage 1: W_hi -- A_hi.W_hi -> main, A_lo.W_hi -> correction ------------------------------------------------
-            wait_b(&bars->wfull[c.stage], c.wpar);
-            if (i == 0) wait_b(&bars->bfull[c.bslot], c.bpar);
+            wait_i(&bars->wfull[c.stage], c.wpar);
+            if (i == 0) wait_i(&bars->bfull[c.bslot], c.bpar);
             tc_fence_after();
             if (elect_one()) {
                 if (i == 0) {      // bias: D = ones[128x16] . tile[NHx16]^T, tile columns (hi, mid, lo, 0, ...); overwrites the accumulator
@@ -225,7 +230,7 @@ __device__ __forceinline__ void issue_layer(IssueCtx& c) {
             if (i == 0) { c.bslot ^= 1; if (c.bslot == 0) c.bpar ^= 1; }
             if (++c.stage == NSTAGE) { c.stage = 0; c.wpar ^= 1; }
             // ---- stage 2: W_lo -- A_hi.W_lo -> correction -------------------------------------------------------------------
-            wait_b(&bars->wfull[c.stage], c.wpar);
+            wait_i(&bars->wfull[c.stage], c.wpar);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t b = c.w_lo + c.stage * (STAGE_BYTES >> 4);
