@@ -55,7 +55,8 @@ def config_parser():
     a("--i_weights", type=int, default=5000); a("--i_testset", type=int, default=1000)
     a("--i_video", type=int, default=5000)
     # B200 build only: arithmetic mode of the FaceNeRF kernel ("fp32" | "bf16")
-    a("--mlp_mode", type=str, default="fp32")
+    a("--mlp_mode", type=str, default="fp32")                       # fp32 (FFMA) | fp16x2 (tensor cores, fp32 gate) | bf16 (tensor cores, PSNR gate)
+    a("--check_numerics", action="store_true")                      # the NaN / Inf report of audio_exp_nerf.py:367-369 (one kernel + one host read)
     return parser
 
 

@@ -248,7 +248,7 @@ class Network(nn.Module):
         perturb = self.args.perturb if perturb is None else perturb
         ret = _render_rays_impl(rays, bc_rgb, self.face_nerf_coarse, self.face_nerf_fine, aud_para, expr, latent_code,
                                 self.args.N_samples, self.args.N_importance, retraw, lindisp, perturb, white_bkgd,
-                                raw_noise_std, pytest)
+                                raw_noise_std, pytest, check_numerics=getattr(self.args, "check_numerics", False))
         return {k: v for k, v in ret.items() if k not in _PRIVATE}
 
     def raw2outputs(self, raw, z_vals, rays_d, bc_rgb, raw_noise_std=0, white_bkgd=False, pytest=False):
