@@ -1435,3 +1435,19 @@ def test_fp16x2_training_falls_back_to_fp32_kernels_and_rejects_small_s(M):
         n_.query(rays, z, b["aud"].to(DEV), b["expr"].to(DEV), b["latent"].to(DEV)).square().sum().backward()
         outs.append(n_.pts_linears[3].weight.grad.clone())
     close(outs[0], outs[1], 1e-5 * float(outs[1].abs().max()), "fp16x2 training gradient == fp32 kernels' (atomic reductions: not bitwise)")
+
+
+def test_conditioning_gradients_keep_input_shapes(M):
+    """aud / expr / latent may arrive as (C,), (1, C) (latent_codes[[idx]], un-squeezed DataLoader tensors): the gradients
+    come back in the inputs' own shapes, in both training modes."""
+    b = O.synthetic_train_batch(0)
+    rays = b["rays"][:8].to(DEV)
+    for mode in ("fp32", "bf16"):
+        net = head_net(M, O.init_face_nerf(7), mode).train()
+        z = M.ops.sample_coarse(rays, 64)
+        aud = b["aud"].to(DEV)[None].clone().requires_grad_(True)                  # (1, 64)
+        expr = b["expr"].to(DEV).clone().requires_grad_(True)                      # (76,)
+        lat = torch.ones(5, 32, device=DEV, requires_grad=True)
+        net.query(rays, z, aud, expr, lat[[3]]).square().sum().backward()          # latent (1, 32) through advanced indexing
+        assert aud.grad.shape == (1, 64) and expr.grad.shape == (76,) and lat.grad.shape == (5, 32)
+        assert float(lat.grad[3].abs().sum()) > 0 and float(lat.grad[[0, 1, 2, 4]].abs().sum()) == 0
