@@ -14,7 +14,7 @@ REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 SO_PATH = os.environ.get("INERF_SO") or os.path.join(PKG_DIR, "libinerf_b200.so")     # INERF_SO: profiling builds only
 SOURCES = ["api.cu", "rays.cu", "composite.cu", "sample_pdf.cu", "mlp_fp32.cu", "mlp_fp32_bwd.cu", "mlp_bf16.cu", "mlp_bf16_bwd.cu",
-           "mlp_bf16_dw.cu", "mlp_f16x2.cu", "audio_net.cu"]
+           "mlp_bf16_dw.cu", "mlp_f16x2.cu", "audio_net.cu", "render_fused.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--shared"]
 
@@ -34,6 +34,27 @@ class InerfNetDims(ctypes.Structure):
 
 ParamArray = ctypes.c_void_p * N_PARAMS
 
+
+class InerfRenderNet(ctypes.Structure):
+    """One FaceNeRF as inerf_render_rays_fused takes it (include/inerf_b200.h)."""
+    _fields_ = [("dims", InerfNetDims), ("params_host", ctypes.POINTER(ctypes.c_void_p)), ("packed", ctypes.c_void_p),
+                ("aud", ctypes.c_void_p), ("expr", ctypes.c_void_p), ("latent", ctypes.c_void_p)]
+
+
+class InerfRenderArgs(ctypes.Structure):
+    _fields_ = ([(k, ctypes.c_int32) for k in ("mode", "n", "n_samples", "n_importance", "perturb", "lindisp", "white_bkgd")] +
+                [("rays", ctypes.c_void_p), ("ray_stride", ctypes.c_int32)] +
+                [(k, ctypes.c_int32) for k in ("gen_rays", "H", "W", "first")] +
+                [(k, ctypes.c_float) for k in ("focal", "cx", "cy", "near_", "far_")] +
+                [("c2w", ctypes.c_void_p), ("c2w_row_stride", ctypes.c_int32), ("bc_rgb", ctypes.c_void_p), ("t_vals", ctypes.c_void_p),
+                 ("u_vals", ctypes.c_void_p), ("rng_state", ctypes.c_void_p), ("coarse", InerfRenderNet), ("fine", InerfRenderNet)] +
+                [(k, ctypes.c_void_p) for k in ("rgb_map", "disp_map", "acc_map", "depth_map", "last_weight", "rgb0", "disp0", "acc0", "z_std",
+                                                "weights", "z_vals", "rgb_map_fg", "rgb_map_fg0", "last_weight0", "nonfinite", "workspace")] +
+                [("workspace_bytes", ctypes.c_size_t)])
+
+
+NF_BITS = {"rgb_map": 1, "disp_map": 2, "acc_map": 4, "rgb0": 8, "disp0": 16, "acc0": 32, "z_std": 64, "last_weight": 128}     # INERF_NF_*
+
 _I, _F, _P, _L, _SZP = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_size_t)
 _DIMS = ctypes.POINTER(InerfNetDims)
 _PARAMS = ctypes.POINTER(ctypes.c_void_p)
@@ -43,6 +64,7 @@ SIGNATURES = {
     "inerf_version": (_I, []),
     "inerf_last_error": (ctypes.c_char_p, []),
     "inerf_device_check": (_I, []),
+    "inerf_sizeof": (ctypes.c_size_t, [_I]),
     "inerf_get_rays": (_I, [_I, _I, _F, _F, _F, _P, _I, _F, _F, _P, _P]),
     "inerf_get_rays_at": (_I, [_P, _I, _F, _F, _F, _P, _I, _F, _F, _P, _P]),
     "inerf_get_rays_range": (_I, [_I, _I, _F, _F, _F, _P, _I, _F, _F, _I, _I, _P, _P]),
@@ -60,6 +82,8 @@ SIGNATURES = {
     "inerf_head_torso_blend": (_I, [_P, _P, _P, _I, _P, _P]),
     "inerf_sample_pdf": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P, _I, _P, _P, _P]),
     "inerf_importance_sample": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P]),
+    "inerf_render_workspace_bytes": (_I, [ctypes.POINTER(InerfRenderArgs), _SZP]),
+    "inerf_render_rays_fused": (_I, [ctypes.POINTER(InerfRenderArgs), _P]),
     "inerf_mlp_cond_floats": (_I, [_DIMS, _SZP]),
     "inerf_mlp_fold_cond": (_I, [_DIMS, _PARAMS, _P, _P, _P, _P, _P]),
     "inerf_mlp_packed_bytes": (_I, [_I, _DIMS, _SZP]),
@@ -141,6 +165,10 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)           # AttributeError here = header/library mismatch
             fn.restype, fn.argtypes = res, args
+        for which, struct in enumerate((InerfNetDims, InerfRenderNet, InerfRenderArgs)):      # the ctypes mirrors must match the header
+            if L.inerf_sizeof(which) != ctypes.sizeof(struct):
+                raise RuntimeError(f"{struct.__name__}: ctypes layout ({ctypes.sizeof(struct)} B) differs from the library's "
+                                   f"({L.inerf_sizeof(which)} B); rebuild libinerf_b200.so")
         _lib = L
     return _lib
 

@@ -19,6 +19,15 @@ extern "C" int inerf_version(void) { return INERF_VERSION; }
 
 extern "C" const char* inerf_last_error(void) { return inerf::g_err; }
 
+extern "C" size_t inerf_sizeof(int which) {
+    switch (which) {
+        case 0: return sizeof(InerfNetDims);
+        case 1: return sizeof(InerfRenderNet);
+        case 2: return sizeof(InerfRenderArgs);
+        default: return 0;
+    }
+}
+
 extern "C" int inerf_device_check(void) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);

@@ -5,41 +5,21 @@
 // reference's tensor-op-at-a-time fp32 values.
 #include "common.cuh"
 #include "philox.cuh"
+#include "rays_parts.cuh"
 
 using namespace inerf;
 
 // ---------------------------------------------------------------------------------------------
 // get_rays + packing.  helper.py:228-243, audio_exp_nerf.py:409-427
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_ray(float* __restrict__ r, float ox, float oy, float oz, float dx, float dy,
-                                          float dz, float near_, float far_) {
-    // viewdirs = d / ||d||_2   (torch.norm = sqrt(sum of squares), then a true division)
-    float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-    r[0] = ox; r[1] = oy; r[2] = oz;
-    r[3] = dx; r[4] = dy; r[5] = dz;
-    r[6] = near_; r[7] = far_;
-    r[8] = __fdiv_rn(dx, nrm); r[9] = __fdiv_rn(dy, nrm); r[10] = __fdiv_rn(dz, nrm);
-}
-
 // rays of the pixels [first, first + count) of the row-major H x W grid; rays[0] is pixel `first`
 __global__ void get_rays_kernel(int W, int first, int count, float focal, float cx, float cy, const float* __restrict__ c2w,
                                 int rs, float near_, float far_, float* __restrict__ rays) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= count) return;
     int row = (first + idx) / W, col = (first + idx) - row * W;
-    // camera-frame direction ((i-cx)/f, -(j-cy)/f, -1)
-    float c0 = __fdiv_rn(__fsub_rn((float)col, cx), focal);
-    float c1 = -__fdiv_rn(__fsub_rn((float)row, cy), focal);
-    float c2 = -1.0f;
     float d[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        // torch.sum(dirs[..., None, :] * c2w[:3,:3], -1): products rounded, added left to right
-        float a = __fmul_rn(c0, c2w[r * rs + 0]);
-        float b = __fmul_rn(c1, c2w[r * rs + 1]);
-        float c = __fmul_rn(c2, c2w[r * rs + 2]);
-        d[r] = __fadd_rn(__fadd_rn(a, b), c);
-    }
+    pixel_dir((float)row, (float)col, focal, cx, cy, c2w, rs, d);
     store_ray(rays + (size_t)idx * 11, c2w[3], c2w[rs + 3], c2w[2 * rs + 3], d[0], d[1], d[2], near_, far_);
 }
 
@@ -58,17 +38,8 @@ __global__ void get_rays_at_kernel(const long long* __restrict__ coords, int n, 
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
     const float row = (float)coords[2 * idx], col = (float)coords[2 * idx + 1];
-    float c0 = __fdiv_rn(__fsub_rn(col, cx), focal);
-    float c1 = -__fdiv_rn(__fsub_rn(row, cy), focal);
-    float c2 = -1.0f;
     float d[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        float a = __fmul_rn(c0, c2w[r * rs + 0]);
-        float b = __fmul_rn(c1, c2w[r * rs + 1]);
-        float c = __fmul_rn(c2, c2w[r * rs + 2]);
-        d[r] = __fadd_rn(__fadd_rn(a, b), c);
-    }
+    pixel_dir(row, col, focal, cx, cy, c2w, rs, d);
     store_ray(rays + (size_t)idx * 11, c2w[3], c2w[rs + 3], c2w[2 * rs + 3], d[0], d[1], d[2], near_, far_);
 }
 
@@ -146,15 +117,6 @@ extern "C" int inerf_posenc(const float* x, int64_t n, int dims, int n_freqs, fl
 // ---------------------------------------------------------------------------------------------
 // stratified coarse depths.  audio_exp_nerf.py:306-328
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float coarse_z(float near_, float far_, float t, int lindisp) {
-    if (!lindisp)   // near * (1. - t) + far * t
-        return __fadd_rn(__fmul_rn(near_, __fsub_rn(1.0f, t)), __fmul_rn(far_, t));
-    // 1. / (1. / near * (1. - t) + 1. / far * t)
-    float a = __fmul_rn(__fdiv_rn(1.0f, near_), __fsub_rn(1.0f, t));
-    float b = __fmul_rn(__fdiv_rn(1.0f, far_), t);
-    return __fdiv_rn(1.0f, __fadd_rn(a, b));
-}
-
 template <bool RNG>
 __global__ void sample_coarse_kernel(const float* __restrict__ rays, int n, int ray_stride, int s,
                                      const float* __restrict__ t_vals, const float* __restrict__ t_rand,

@@ -4,6 +4,7 @@ PyTorch supplies device memory, streams and autograd bookkeeping only; every op 
 hand-written CUDA kernel launched through ctypes on the current stream.
 """
 import ctypes
+import os
 
 import torch
 
@@ -14,6 +15,8 @@ _tables = {}
 
 # ---- launch accounting (bench.py reads these; one entry per C-ABI kernel launch) -----------------
 LAUNCHES = {"count": 0}
+# inference render_rays through the single fused entry point (inerf_render_rays_fused); INERF_FUSED_RENDER=0 keeps the stage-by-stage calls
+FUSED_RENDER = os.environ.get("INERF_FUSED_RENDER", "1") != "0"
 _timing = None          # None, or dict name -> list of (start_event, end_event)
 
 
@@ -35,9 +38,9 @@ class kernel_timing:
         return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.events.items()}
 
 
-def call(name, fn, *args):
-    """Launch one C-ABI entry point: count it, optionally bracket it with events, raise on error."""
-    LAUNCHES["count"] += 1
+def call(name, fn, *args, launches=1):
+    """Launch one C-ABI entry point: count its kernel launches, optionally bracket it with events, raise on error."""
+    LAUNCHES["count"] += launches
     if _timing is None:
         check(fn(*args), name)
         return
@@ -385,6 +388,94 @@ def importance_sample(z_coarse, w_coarse, u, policy=_lib.INERF_PDF_EXACT_TORCH_C
         call("inerf_importance_sample", _lib.lib().inerf_importance_sample, ptr(z_coarse), ptr(w_coarse), n, s1, n_imp, ptr(u), per_ray, policy,
                                                  ptr(zs), ptr(inds), ptr(zm), ptr(zstd), stream())
     return zs, zm, zstd, inds
+
+
+# ------------------------------------------------------------------------------------------------
+# the whole inference render_rays in one C call
+# ------------------------------------------------------------------------------------------------
+
+def _render_net(net, aud, expr, latent, keep):
+    """InerfRenderNet of one FaceNeRF module; `keep` collects every object whose memory the struct points into."""
+    params = [p.detach() for p in net._prep(aud, expr, latent)]
+    packed = net.packed_weights(net.kernel_params())
+    arr = param_array(params)
+    f = lambda t, d: f32c(t.detach(), "conditioning").reshape(-1) if d > 0 else None
+    a, e, l = f(aud, net.dim_aud), f(expr, net.dim_expr), f(latent, net.dim_latent)
+    keep += [params, packed, arr, a, e, l]
+    r = _lib.InerfRenderNet()
+    r.dims = net._dims
+    r.params_host = ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p))
+    r.packed = packed.data_ptr() if packed is not None else None
+    r.aud, r.expr, r.latent = (t.data_ptr() if t is not None else None for t in (a, e, l))
+    return r
+
+
+def render_rays_fused(net_coarse, net_fine, cond_coarse, cond_fine, bc_rgb, n_samples, n_importance, perturb, rays=None, gen=None,
+                      lindisp=False, white_bkgd=False, with_fg=False, want_weights=False, want_z=False, check_numerics=False, state=None):
+    """Network.render_rays under no_grad as ONE C call (inerf_render_rays_fused): five kernel launches in the reference's
+    configuration (set-up, coarse FaceNeRF, compositor + sampler, fine FaceNeRF, final compositor).  rays: packed (n, 11), or
+    gen = dict(H, W, focal, cx, cy, near, far, c2w, first, count) to generate the rays of pixels [first, first + count) on the fly.
+    cond_*: (aud, expr, latent) of each net.  Returns the render_rays dict (plus '_nonfinite' bits when check_numerics)."""
+    mode = net_coarse._mode()
+    bc_rgb = f32c(bc_rgb, "bc_rgb")
+    dev = bc_rgb.device
+    keep = []
+    a = _lib.InerfRenderArgs()
+    a.mode, a.n_samples, a.n_importance = mode, int(n_samples), int(n_importance)
+    a.perturb, a.lindisp, a.white_bkgd = int(perturb > 0.), int(bool(lindisp)), int(bool(white_bkgd))
+    if gen is not None:
+        c2w = f32c(gen["c2w"], "c2w")
+        n = int(gen["count"])
+        a.gen_rays, a.H, a.W, a.first = 1, int(gen["H"]), int(gen["W"]), int(gen["first"])
+        a.focal, a.cx, a.cy, a.near_, a.far_ = float(gen["focal"]), float(gen["cx"]), float(gen["cy"]), float(gen["near"]), float(gen["far"])
+        a.c2w, a.c2w_row_stride = c2w.data_ptr(), c2w.stride(0)
+        keep.append(c2w)
+    else:
+        rays = f32c(rays, "rays")
+        n = rays.shape[0]
+        a.rays, a.ray_stride = rays.data_ptr(), rays.shape[1]
+    a.n = n
+    assert bc_rgb.shape == (n, 3), f"bc_rgb {tuple(bc_rgb.shape)} for {n} rays"
+    a.bc_rgb = bc_rgb.data_ptr()
+    t_vals, u_vals = linspace_table(n_samples, dev), linspace_table(n_importance, dev)
+    a.t_vals, a.u_vals = t_vals.data_ptr(), u_vals.data_ptr()
+    if a.perturb:
+        state = rng_state(dev) if state is None else state
+        a.rng_state = state.data_ptr()
+    a.coarse = _render_net(net_coarse, *cond_coarse, keep)
+    a.fine = _render_net(net_fine, *cond_fine, keep)
+    stot = n_samples + n_importance
+    out = torch.empty((n * (13 + (7 if with_fg else 0)),), device=dev)
+    cuts = [("rgb_map", 3), ("disp_map", 1), ("acc_map", 1), ("depth_map", 1), ("last_weight", 1), ("rgb0", 3), ("disp0", 1), ("acc0", 1),
+            ("z_std", 1)] + ([("rgb_map_fg", 3), ("rgb_map_fg0", 3), ("last_weight0", 1)] if with_fg else [])
+    ret, o = {}, 0
+    for k, w in cuts:
+        ret[k] = out[o:o + n * w].view(n, 3) if w == 3 else out[o:o + n]
+        setattr(a, k, ret[k].data_ptr())
+        o += n * w
+    if want_weights:
+        ret["_weights"] = torch.empty((n, stot), device=dev)
+        a.weights = ret["_weights"].data_ptr()
+    if want_z:
+        ret["_z_vals"] = torch.empty((n, stot), device=dev)
+        a.z_vals = ret["_z_vals"].data_ptr()
+    flag = None
+    if check_numerics:
+        flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+        a.nonfinite = flag.data_ptr()
+    nb = ctypes.c_size_t()
+    check(_lib.lib().inerf_render_workspace_bytes(ctypes.byref(a), ctypes.byref(nb)), "inerf_render_workspace_bytes")
+    ws = torch.empty((max(nb.value, 1),), device=dev, dtype=torch.uint8)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), nb.value
+    if n > 0:
+        with torch.cuda.device(dev):
+            fast = a.perturb and n_samples == 64 and n_importance == 128 and not lindisp
+            call("inerf_render_rays_fused", _lib.lib().inerf_render_rays_fused, ctypes.byref(a), stream(), launches=5 if fast else 7)
+    ret["_depth_map"] = ret.pop("depth_map")
+    if flag is not None:
+        bits = int(flag.item())
+        ret["_nonfinite"] = [k for k, b in _lib.NF_BITS.items() if bits & b]
+    return ret
 
 
 # ------------------------------------------------------------------------------------------------

@@ -58,10 +58,35 @@ def raw2outputs_torso(raw, z_vals, rays_d, bc_rgb, raw_noise_std=0, white_bkgd=F
 # ------------------------------------------------------------------------------------------------
 # the path
 # ------------------------------------------------------------------------------------------------
+def _fusable(net_coarse, net_fine, aud, expr, latent, N_samples, N_importance, retraw=False, raw_noise_std=0., pytest=False,
+             pdf_policy=_lib.INERF_PDF_EXACT_TORCH_CPU):
+    """True when the call can run as inerf_render_rays_fused: an inference call (autograd not recording anything the nets could need)
+    of a two-pass shape the fused entry takes, without the extras that materialise per-sample tensors (retraw, noise, pytest tables).
+    Per-kernel event timing (ops.kernel_timing) keeps the stage-by-stage path so that every kernel gets its own event pair."""
+    if ops._timing is not None or retraw or raw_noise_std > 0. or pytest or not ops.FUSED_RENDER or pdf_policy != _lib.INERF_PDF_EXACT_TORCH_CPU:
+        return False
+    if not (N_importance > 0 and N_samples >= 4 and N_samples % 2 == 0 and (N_samples + N_importance) % 2 == 0 and N_samples + N_importance <= 256):
+        return False
+    if net_coarse.mlp_mode != net_fine.mlp_mode:
+        return False
+    cond = (aud, expr, latent)
+    return not any(FaceNeRF._wants_grad(n.kernel_params(), *cond) for n in (net_coarse, net_fine))
+
+
 def _render_rays_impl(rays, bc_rgb, net_coarse, net_fine, aud, expr, latent, N_samples, N_importance, retraw=False,
                       lindisp=False, perturb=0., white_bkgd=False, raw_noise_std=0., pytest=False, with_fg=False,
-                      pdf_policy=_lib.INERF_PDF_EXACT_TORCH_CPU, check_numerics=False):
-    """audio_exp_nerf.py:297-371 (torso extras: train_torso.py:290-363)."""
+                      pdf_policy=_lib.INERF_PDF_EXACT_TORCH_CPU, check_numerics=False, gen=None):
+    """audio_exp_nerf.py:297-371 (torso extras: train_torso.py:290-363).  gen: instead of `rays`, the frame / camera / pixel range whose
+    rays the fused entry generates itself (frame.FrameRenderer)."""
+    net_f = net_coarse if net_fine is None else net_fine
+    if gen is not None or _fusable(net_coarse, net_f, aud, expr, latent, N_samples, N_importance, retraw, raw_noise_std, pytest, pdf_policy):
+        # inference: the whole call is ONE C entry point (inerf_render_rays_fused), five launches in the reference's configuration
+        ret = ops.render_rays_fused(net_coarse, net_f, (aud, expr, latent), (aud, expr, latent), bc_rgb, N_samples, N_importance, perturb,
+                                    rays=rays, gen=gen, lindisp=lindisp, white_bkgd=white_bkgd, with_fg=with_fg,
+                                    check_numerics=check_numerics)
+        for k in ret.get('_nonfinite', ()):
+            logger.info(f"! [Numerical Error] {k} contains nan or inf.")
+        return ret
     rays = ops.f32c(rays, "rays")
     bc_rgb = ops.f32c(bc_rgb, "bc_rgb")
     if rays.shape[-1] <= 8:

@@ -86,6 +86,9 @@ int inerf_version(void);
 const char* inerf_last_error(void);
 /* 0 when the current CUDA device is compute capability 10.x, INERF_E_DEVICE otherwise. */
 int inerf_device_check(void);
+/* sizeof of the structs of this header as the library was compiled: 0 InerfNetDims, 1 InerfRenderNet, 2 InerfRenderArgs (0 for any
+ * other value) -- lets a foreign-language binding check its struct layout at load time. */
+size_t inerf_sizeof(int which);
 
 /* ---- rays ----------------------------------------------------------------------------------- */
 
@@ -204,6 +207,69 @@ int inerf_importance_sample(const float* z_coarse, const float* w_coarse, int n,
 int inerf_importance_sample_rng(const float* z_coarse, const float* w_coarse, int n, int s1, int n_imp,
                                 const uint64_t* rng_state, uint32_t stream_id, float* z_samples, float* z_merged,
                                 float* z_std, void* stream);
+
+/* ---- the whole inference render_rays in one call ------------------------------------------------------------------------------
+ * Network.render_rays under torch.no_grad() (audio_exp_nerf.py:297-371; the torso variant train_torso.py:290-363 with rgb_map_fg !=
+ * NULL): stratified depths -> coarse FaceNeRF -> raw2outputs -> sample_pdf + sort + std -> fine FaceNeRF -> raw2outputs, enqueued by
+ * ONE entry point on one stream.  In the reference's configuration (64 + 128 samples, perturb > 0) that is FIVE launches per call
+ * instead of ten, and neither the coarse weights nor the fine weights nor a tensor of draws reach HBM:
+ *   1. set-up kernel: conditioning fold of BOTH nets + (optionally) the rays of pixels [first, first + n) + the jittered coarse depths;
+ *   2. coarse FaceNeRF (inerf_mlp_fwd's kernel);
+ *   3. compositor + importance sampler in one kernel: the weights go from the compositor's registers into the sampler's CDF scan;
+ *   4. fine FaceNeRF;
+ *   5. final compositor: maps + last_weight only (no (n, S) weights tensor unless asked for), the NaN / Inf flags of
+ *      audio_exp_nerf.py:367-369 and the bump of the RNG offset.
+ * Other shapes / perturb == 0 run the stand-alone kernels of this header inside the same call (deterministic depths keep the
+ * bit-exact sample_pdf policy), so results are bit-identical to calling the stages one by one.
+ * Needs n_importance > 0, an even n_samples >= 4 and an even n_samples + n_importance <= 256; raw_noise_std == 0. */
+typedef struct InerfRenderNet {
+    InerfNetDims dims;
+    const float* const* params_host; /* INERF_N_PARAMS device pointers (host array)            */
+    const void* packed;              /* inerf_mlp_pack blob for `mode` (NULL for INERF_MLP_FP32) */
+    const float* aud;                /* conditioning vectors (device), NULL where the dim is 0  */
+    const float* expr;
+    const float* latent;
+} InerfRenderNet;
+
+/* bits of *nonfinite (the keys the reference scans, audio_exp_nerf.py:367-369) */
+enum {
+    INERF_NF_RGB_MAP = 1, INERF_NF_DISP_MAP = 2, INERF_NF_ACC_MAP = 4, INERF_NF_RGB0 = 8, INERF_NF_DISP0 = 16, INERF_NF_ACC0 = 32,
+    INERF_NF_Z_STD = 64, INERF_NF_LAST_WEIGHT = 128
+};
+
+typedef struct InerfRenderArgs {
+    int32_t mode;                    /* INERF_MLP_FP32 / _BF16 / _F16X2, both nets                                        */
+    int32_t n;                       /* rays                                                                               */
+    int32_t n_samples, n_importance; /* args.N_samples, args.N_importance                                                  */
+    int32_t perturb;                 /* 0: deterministic depths; 1: stratified jitter and importance draws made in-kernel  */
+    int32_t lindisp, white_bkgd;
+    /* rays: supplied (n, ray_stride >= 11) as inerf_pack_rays / inerf_get_rays write them, or -- gen_rays != 0 -- generated here for
+     * the pixels [first, first + n) of the H x W frame (inerf_get_rays_range's arguments) into the workspace */
+    const float* rays;
+    int32_t ray_stride;
+    int32_t gen_rays, H, W, first;
+    float focal, cx, cy, near_, far_;
+    const float* c2w;
+    int32_t c2w_row_stride;
+    const float* bc_rgb;             /* (n, 3)                                                                             */
+    const float* t_vals;             /* torch.linspace(0, 1, n_samples) (host-generated table)                             */
+    const float* u_vals;             /* torch.linspace(0, 1, n_importance); only read when perturb == 0                    */
+    uint64_t* rng_state;             /* {seed, offset}; only used when perturb != 0; the offset is advanced by 1           */
+    InerfRenderNet coarse, fine;
+    /* outputs (device).  Required: rgb_map (n,3), disp_map, acc_map, depth_map, last_weight (n), rgb0 (n,3), disp0, acc0, z_std (n).
+     * Optional (NULL to skip): weights (n, S) of the fine pass, z_vals (n, S) merged depths, and the torso extras rgb_map_fg (n,3),
+     * rgb_map_fg0 (n,3), last_weight0 (n) -- the three are given together or not at all. */
+    float *rgb_map, *disp_map, *acc_map, *depth_map, *last_weight, *rgb0, *disp0, *acc0, *z_std;
+    float *weights, *z_vals, *rgb_map_fg, *rgb_map_fg0, *last_weight0;
+    int32_t* nonfinite;              /* NULL or a device int32: INERF_NF_* bits are OR-ed in (not cleared here)            */
+    void* workspace;                 /* device scratch of inerf_render_workspace_bytes bytes, 256-byte aligned             */
+    size_t workspace_bytes;
+} InerfRenderArgs;
+
+/* Scratch the call needs for these shapes (rays when generated, both conditioning buffers, coarse depths, raw of both passes, merged
+ * depths, and the coarse weights / samples of the deterministic path). */
+int inerf_render_workspace_bytes(const InerfRenderArgs* args, size_t* bytes);
+int inerf_render_rays_fused(const InerfRenderArgs* args, void* stream);
 
 /* ---- FaceNeRF MLP --------------------------------------------------------------------------- */
 

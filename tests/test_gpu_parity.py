@@ -1164,6 +1164,74 @@ def test_nonfinite_flag(M, golden):
     assert "rgb_map" in r["_nonfinite"] and ok["_nonfinite"] == []
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_fused_render_entry_bit_matches_stage_calls(M, golden, mode):
+    """inerf_render_rays_fused (ONE C call, five launches in the reference's configuration) against the stage-by-stage entry points the
+    parity tests above pin to the reference: every output bit for bit -- deterministic depths (bit-exact sample_pdf policy), in-kernel
+    draws (same Philox state), lindisp / a 48 + 80 shape (stand-alone kernels inside the fused call), the torso extras, rays generated
+    by the set-up kernel, the NaN flags -- and the RNG offset advances by one either way."""
+    from ideal_nerf_b200 import ops
+    from ideal_nerf_b200.render import _render_rays_impl
+    g = golden("render_3072")
+    net = _preset_nets(M, g, "dense", mode)
+    n = 1003                                                  # not a multiple of the 8 rays per block
+    rays, bc = C(g["rays"])[:n], C(g["bc_rgb"])[:n]
+    aud, expr, lat = C(g["aud"]), C(g["expr"]), C(g["latent"])
+
+    def run(fused, **kw):
+        ops.FUSED_RENDER = fused
+        ops.seed_rng(1234, DEV, offset=7)
+        before = ops.LAUNCHES["count"]
+        try:
+            with torch.no_grad():
+                r = _render_rays_impl(kw.pop("rays", rays), bc, net.face_nerf_coarse, net.face_nerf_fine, aud, expr, lat,
+                                      kw.pop("S", 64), kw.pop("NI", 128), **kw)
+        finally:
+            ops.FUSED_RENDER = True
+        return r, int(ops.rng_state(DEV)[1].item()), ops.LAUNCHES["count"] - before
+
+    cases = [dict(perturb=0.), dict(perturb=1.), dict(perturb=1., lindisp=True), dict(perturb=1., white_bkgd=True, with_fg=True),
+             dict(perturb=0., with_fg=True), dict(perturb=1., S=48, NI=80), dict(perturb=1., check_numerics=True)]
+    for kw in cases:
+        a, off_a, launches = run(True, **dict(kw))
+        b, off_b, _ = run(False, **dict(kw))
+        keys = [k for k in b if not k.startswith("_") or k in ("_depth_map", "_nonfinite")]
+        assert set(keys) <= set(a), (kw, set(keys) - set(a))
+        for k in keys:
+            if k == "_nonfinite":
+                assert a[k] == b[k] == [], (kw, a[k], b[k])
+            else:
+                assert bits_equal(a[k], b[k]), (mode, kw, k, maxabs(a[k], b[k]))
+        assert off_a == off_b == (8 if kw["perturb"] else 7), (kw, off_a, off_b)
+        if kw == dict(perturb=1.):
+            assert launches == 5, launches
+    # rays generated inside the fused call (frame.FrameRenderer) == rays from inerf_get_rays_range handed to the stage path
+    cam = O.synthetic_camera()
+    first, count = 450 * 200 + 17, 515
+    c2w = cam["c2w"][:3, :4].to(DEV)
+    gen = dict(H=450, W=450, focal=cam["focal"], cx=225., cy=225., near=O.NEAR, far=O.FAR, c2w=c2w, first=first, count=count)
+    bc2 = torch.rand(count, 3, device=DEV)
+    r_rays = ops.get_rays_range(450, 450, cam["focal"], c2w, O.NEAR, O.FAR, first, count)
+    for perturb in (0., 1.):
+        ops.seed_rng(99, DEV)
+        with torch.no_grad():
+            a = _render_rays_impl(None, bc2, net.face_nerf_coarse, net.face_nerf_fine, aud, expr, lat, 64, 128, perturb=perturb, gen=gen)
+        ops.seed_rng(99, DEV)
+        ops.FUSED_RENDER = False
+        try:
+            with torch.no_grad():
+                b = _render_rays_impl(r_rays, bc2, net.face_nerf_coarse, net.face_nerf_fine, aud, expr, lat, 64, 128, perturb=perturb)
+        finally:
+            ops.FUSED_RENDER = True
+        for k in ("rgb_map", "disp_map", "acc_map", "rgb0", "z_std", "last_weight"):
+            assert bits_equal(a[k], b[k]), ("gen", perturb, k)
+    # a NaN audio code through the fused kernels' own flags (perturb > 0: compositor + sampler and the final compositor OR the bits)
+    bad = aud.clone(); bad[3] = float("nan")
+    with torch.no_grad():
+        r = _render_rays_impl(rays[:64], bc[:64], net.face_nerf_coarse, net.face_nerf_fine, bad, expr, lat, 64, 128, perturb=1., check_numerics=True)
+    assert {"rgb_map", "rgb0"} <= set(r["_nonfinite"]), r["_nonfinite"]
+
+
 def test_head_torso_frame_band_config4(M):
     """BASELINE.json config 4 at frame size: the head + torso composited 450 x 450 frame (test_torso.py:516-523; torso rays from the
     frame-0 camera, train_torso.py:132-134) -- three image rows of the frame against the oracle, fp32 mode, <= 1e-3."""

@@ -52,6 +52,35 @@ def test_argument_validation_without_gpu(M):
     assert L.inerf_mlp_fwd(7, ctypes.byref(ok), None, None, None, None, 11, None, 1, 1, None, None) == -1
 
 
+def test_fused_render_entry_validates_without_gpu(M):
+    """inerf_render_rays_fused / inerf_render_workspace_bytes: struct layout agrees with the header, shapes are checked before any
+    device work, and the workspace plan is the sum of the buffers DESIGN.md lists."""
+    L = M.lib()
+    from ideal_nerf_b200._lib import InerfNetDims, InerfRenderArgs, InerfRenderNet
+    assert [L.inerf_sizeof(i) for i in range(4)] == [ctypes.sizeof(InerfNetDims), ctypes.sizeof(InerfRenderNet), ctypes.sizeof(InerfRenderArgs), 0]
+    a = InerfRenderArgs()
+    nb = ctypes.c_size_t()
+    assert L.inerf_render_workspace_bytes(None, ctypes.byref(nb)) == -1
+    a.n, a.n_samples, a.n_importance = 100, 64, 0
+    assert L.inerf_render_workspace_bytes(ctypes.byref(a), ctypes.byref(nb)) == -2            # coarse-only renders use the stage entry points
+    a.n_importance = 128
+    assert L.inerf_render_workspace_bytes(ctypes.byref(a), ctypes.byref(nb)) == -4            # dims not set: unsupported geometry
+    for net in (a.coarse, a.fine):
+        net.dims = InerfNetDims(64, 76, 32, 256, 8, 63, 27)
+    a.perturb = 1
+    assert L.inerf_render_workspace_bytes(ctypes.byref(a), ctypes.byref(nb)) == 0
+    up = lambda b: (b + 255) // 256 * 256
+    cond = (8 * 256 + 3 * 128 + 4) * 4 + 2 * (16 * 4096 + 6 * 2048)
+    want = 2 * up(cond) + up(100 * 64 * 4) + up(100 * 64 * 16) + up(100 * 192 * 4) + up(100 * 192 * 16) + up(100 * 4)
+    assert nb.value == want, (nb.value, want)
+    a.gen_rays, a.perturb = 1, 0                                                               # + rays, coarse weights, z_samples
+    assert L.inerf_render_workspace_bytes(ctypes.byref(a), ctypes.byref(nb)) == 0
+    assert nb.value == want + up(100 * 11 * 4) + up(100 * 64 * 4) + up(100 * 128 * 4)
+    assert L.inerf_render_rays_fused(ctypes.byref(a), None) == -1 and b"workspace" in L.inerf_last_error()
+    a.n = 0
+    assert L.inerf_render_rays_fused(ctypes.byref(a), None) == 0                               # empty batch: nothing to enqueue
+
+
 def test_no_cpu_fallback(M):
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         M.raw2outputs(torch.zeros(2, 4, 4), torch.zeros(2, 4), torch.zeros(2, 3), torch.zeros(2, 3))
