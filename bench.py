@@ -555,6 +555,8 @@ def run_ours(args):
             "config": {"workload": "HeadNeRF full 450x450 frame render (coarse 64 + fine 192 samples), FaceNeRF dim_aud=64 dim_expr=76",
                        "frames_per_step": frames, "rays_per_rank_per_step": (hi - lo) * frames, "mlp_mode": args.mode,
                        "perturb": 1.0, "rng": "in-kernel Philox4x32-10 (stratified jitter + importance draws)",
+                       "entry": "inerf_render_rays_fused: one C call and 5 kernel launches per render_rays (set-up, coarse FaceNeRF, "
+                                "compositor + sampler, fine FaceNeRF, final compositor)",
                        "l2": "inputs larger than L2 (raw 207+622 MB per frame pass)",
                        "parallelism": f"rays block-partitioned over {world} GPU(s), one NCCL all-gather of the bands per frame"},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d * frames,
@@ -565,7 +567,8 @@ def run_ours(args):
                          "frac": (achieved / peak) if achieved else None, "traffic": mlp_traffic(),
                          "peak_kind": f"bf16 dense sustained, {pk_kind}", "launches": n_mlp, "kernel_ms_total": mlp_ms,
                          "share_of_step": mlp_ms / timed_ms_events if timed_ms_events else None,
-                         "how": "second pass of the same steps with a CUDA-event pair around every launch; `value` is the event-free pass"},
+                         "how": "second pass of the same steps through the stage-by-stage entry points with a CUDA-event pair around every launch "
+                                "(the same FaceNeRF kernel); `value` is the event-free pass through inerf_render_rays_fused"},
             "roofline_composite": {"bound": "hbm", "kernel": "inerf_composite_fwd",
                                    "achieved": sa_bytes / (sa_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                    "frac": sa_bytes / (sa_ms * 1e-3) / 1e9 / pk["hbm_gbs"],

@@ -37,6 +37,11 @@ namespace {
 
 constexpr int NSTAGE = 3;
 constexpr int STAGE_BYTES = 16384;
+// CTA-pair build (PAIR = true): every weight stage is split across the two CTAs of a cluster (each holds HALF of its rows), so the same
+// 48 KB ring is six stages deep
+constexpr int NSTAGE_PAIR = 6;
+constexpr int STAGE_BYTES_PAIR = 8192;
+template <bool PAIR> struct RingOf { static constexpr int N = PAIR ? NSTAGE_PAIR : NSTAGE, BYTES = PAIR ? STAGE_BYTES_PAIR : STAGE_BYTES; };
 constexpr int MAX_STEPS = 80;
 constexpr int RMAX = 4;            // rays a 128-row slot can touch (s >= 43)
 constexpr int NTHREADS_BF16 = 512;
@@ -85,21 +90,24 @@ constexpr int OFF_RW = OFF_AW + 1024;                    // rgb_linear.weight 3x
 constexpr int OFF_DIRB = OFF_RW + 1536;                  // [2][RMAX][128] floats
 constexpr int OFF_BAR = OFF_DIRB + 2 * RMAX * 128 * 4;   // mbarriers
 constexpr int BIAS_TILE_BYTES_TOTAL = 16 * 4096 + 6 * 2048;   // per call, after the 2436 folded fp32 biases of `cond`
-constexpr int SMEM_BYTES = OFF_BAR + 256;
+constexpr int SMEM_BYTES = OFF_BAR + 320;
 constexpr int SMEM_ALLOC = SMEM_BYTES;
 static_assert(SMEM_ALLOC <= 232448, "shared memory budget");
 
 struct Bars {
-    uint64_t wfull[NSTAGE], wempty[NSTAGE];
-    uint64_t cbar[3];        // C0, C1, C2   (tcgen05.commit, once per layer)
-    uint64_t ebar[2];        // E0, E1       (8 epilogue warps, once per layer)
-    uint64_t pe_ready;       // 128 PE threads, once per iteration
+    uint64_t wfull[NSTAGE_PAIR], wempty[NSTAGE_PAIR];
+    uint64_t pfull[NSTAGE_PAIR];   // pair build, leader only: the PEER's half of the stage has landed (relayed by the peer's warp 1)
+    uint64_t cbar[3];        // C0, C1, C2   (tcgen05.commit, once per layer; pair build: multicast to both CTAs)
+    uint64_t ebar[2];        // E0, E1       (8 epilogue warps, once per layer; pair build: the leader's, 8 + 8 warps)
+    uint64_t pe_ready;       // 128 PE threads, once per iteration (pair build: the leader's, 4 + 4 warps)
     uint64_t pe_free;        // commit after the last MMA that reads the PE block
     uint64_t dirb_ready;     // 128 PE threads
     uint64_t dirb_free;      // 8 epilogue warps
     uint64_t bfull[2], bempty[2];   // bias-tile ring
+    uint64_t pbfull[2];      // pair build, leader only: the peer's half of the bias tile has landed
     uint32_t tmem_base;
 };
+static_assert(sizeof(Bars) <= 320, "barrier block");
 
 // Hang diagnostics (trace build only): every mbarrier wait has a ~1 s clock64 budget; the first waiter that
 // runs out records {site code, block, thread, aux...} in a host-mapped buffer and traps.  The production build
@@ -124,6 +132,22 @@ __device__ __forceinline__ void wait_or_report(uint64_t* bar, uint32_t parity, i
             }
         }
     }
+}
+
+// Light phase timers of the PRODUCTION kernel (builds with -DINERF_PHASE_TIMERS only; profiles/mlp_phase_timers.py): two clock reads per
+// epilogue half in ONE warp and around the issuer's epilogue-event / weight waits -- the TRACE build's timers inflate an iteration by 50 %.
+#ifdef INERF_PHASE_TIMERS
+__device__ unsigned long long g_phase[148][16];
+#define PH_CLK() clock64()
+#else
+#define PH_CLK() 0ll
+#endif
+
+// issuer-side wait on an event whose arrivals may come from the peer CTA (pair build: cluster-scope acquire)
+template <bool DBG, bool PAIR>
+__device__ __forceinline__ void wait_ev(uint64_t* bar, uint32_t parity, int code, int aux0, int aux1) {
+    if constexpr (PAIR) mbar_wait_cluster(bar, parity);
+    else wait_or_report<DBG>(bar, parity, code, aux0, aux1);
 }
 
 struct LayerInfo { int N, bias_off; };
@@ -154,11 +178,11 @@ __device__ __forceinline__ void epi_convert(const uint32_t (&r)[32], uint32_t* _
         }
         if constexpr (KIND == 1) {
             const float4 w = *reinterpret_cast<const float4*>(aw + j);
-            alpha = fmaf(fmaxf(v[0], 0.f), w.x, alpha); alpha = fmaf(fmaxf(v[1], 0.f), w.y, alpha);
-            alpha = fmaf(fmaxf(v[2], 0.f), w.z, alpha); alpha = fmaf(fmaxf(v[3], 0.f), w.w, alpha);
+            alpha = fmaf(relu_nan(v[0]), w.x, alpha); alpha = fmaf(relu_nan(v[1]), w.y, alpha);
+            alpha = fmaf(relu_nan(v[2]), w.z, alpha); alpha = fmaf(relu_nan(v[3]), w.w, alpha);
         }
         if constexpr (KIND == 3) {
-            const float q[4] = {fmaxf(v[0], 0.f), fmaxf(v[1], 0.f), fmaxf(v[2], 0.f), fmaxf(v[3], 0.f)};
+            const float q[4] = {relu_nan(v[0]), relu_nan(v[1]), relu_nan(v[2]), relu_nan(v[3])};
             const float4 w0 = *reinterpret_cast<const float4*>(rw + j);
             const float4 w1 = *reinterpret_cast<const float4*>(rw + 128 + j);
             const float4 w2 = *reinterpret_cast<const float4*>(rw + 256 + j);
@@ -169,7 +193,7 @@ __device__ __forceinline__ void epi_convert(const uint32_t (&r)[32], uint32_t* _
         packed16[(j >> 1)] = pack_bf16x2_relu(v[0], v[1]);
         packed16[(j >> 1) + 1] = pack_bf16x2_relu(v[2], v[3]);
         if constexpr (TRACE) {
-            if (dump) { tr[j] = fmaxf(v[0], 0.f); tr[j + 1] = fmaxf(v[1], 0.f); tr[j + 2] = fmaxf(v[2], 0.f); tr[j + 3] = fmaxf(v[3], 0.f); }
+            if (dump) { tr[j] = relu_nan(v[0]); tr[j + 1] = relu_nan(v[1]); tr[j + 2] = relu_nan(v[2]); tr[j + 3] = relu_nan(v[3]); }
         }
     }
 }
@@ -200,6 +224,27 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, u
         : "memory");
 }
 
+// The same for a CTA pair: M = 256 (128 rows from each CTA), the N rows of B split across the two CTAs; issued by the leader only.
+__device__ __forceinline__ void umma_bf16_lohi_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+template <bool PAIR>
+__device__ __forceinline__ void umma_any(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (PAIR) umma_bf16_lohi_pair(tmem_d, a_lo, b_lo, hi, idesc, accumulate);
+    else umma_bf16_lohi(tmem_d, a_lo, b_lo, hi, idesc, accumulate);
+}
+template <bool PAIR>
+__device__ __forceinline__ void commit_any(uint64_t* bar) {
+    if constexpr (PAIR) umma_commit_pair(bar);
+    else umma_commit(bar);
+}
+
 // Descriptor halves of a K-major, NON-swizzled 16-column (K = 16) bf16 tile stored as [row/8][k/8][row%8][k%8]: 8x8 core matrices of
 // 128 contiguous bytes, the two K halves 128 B apart (leading byte offset), 8-row groups 256 B apart (stride byte offset).
 constexpr uint32_t HI_NOSWZ = (256u >> 4) | (1u << 14);
@@ -212,6 +257,7 @@ struct IssueCtx {
     uint32_t stage, wpar;                // weight ring position and the parity of its current round
     uint32_t ones_lo, bt_lo, bslot, bpar;   // bias MMA operands (no-swizzle descriptors) and the bias ring position
     uint32_t layer_ctr, iter_ctr;
+    long long ph_e0, ph_e1, ph_e_other, ph_w;      // INERF_PHASE_TIMERS build: cycles waiting for E0 / E1 of a 256-wide layer after a 256-wide one, other layers' events, weight stages
     long long t_e, t_w, t_pe;            // trace build: where the issuer waits
     long long t_e_layer[11];             // ... and the epilogue-event waits per layer
 };
@@ -220,13 +266,14 @@ struct IssueCtx {
 // constant of (L, half, K-block), so a step costs ~10 uniform-datapath instructions per tcgen05.mma instead of a table decode.
 // (The table-driven form was issue-latency bound: ~150 dependent SASS instructions per 8-MMA step on ONE thread, ~1000 cycles
 // against the 512 the tensor pipe needs -- profiles/r01_mlp_ablation.txt.)
-template <int L, bool TRACE, int ABL>
+template <int L, bool TRACE, int ABL, bool PAIR>
 __device__ __forceinline__ void issue_layer(IssueCtx& c) {
+    constexpr int NSTAGE = RingOf<PAIR>::N, STAGE_BYTES = RingOf<PAIR>::BYTES;
     constexpr int N = lay_N(L), NH = N / 2, NKB = lay_act_kb(L), CNT = NKB + (lay_pe(L) ? 1 : 0);
     constexpr int KB_PER_HALF_PREV = lay_prev_N(L) / 128;     // activation K-blocks written by ONE half of the previous epilogue
     constexpr int N_OUT_H0 = NH / 64;                          // K-blocks epi(h0) of THIS layer overwrites
     constexpr int N_FIRST = NKB < N_OUT_H0 ? NKB : N_OUT_H0;   // leading K-blocks of h1 that epi(h0) will overwrite
-    constexpr uint32_t IDESC = umma_idesc_bf16(128, NH);
+    constexpr uint32_t IDESC = umma_idesc_bf16(PAIR ? 256 : 128, NH);
     Bars* bars = c.bars;
     const uint32_t par_prev = (c.layer_ctr - 1) & 1;
 #pragma unroll
@@ -238,20 +285,31 @@ __device__ __forceinline__ void issue_layer(IssueCtx& c) {
             if constexpr (TRACE) c0 = clock64();
             if (h == 0 && c.layer_ctr > 0) {                   // each epilogue event is waited ONCE per layer, at its first use
                 if (L == 0) {                                  // new iteration: both accumulator halves of V2 drained
-                    if (i == 0) { wait_or_report<TRACE>(&bars->ebar[0], par_prev, 201, L, (int)c.layer_ctr);
-                                  wait_or_report<TRACE>(&bars->ebar[1], par_prev, 202, L, (int)c.layer_ctr); }
+                    if (i == 0) { const long long p0 = PH_CLK();
+                                  wait_ev<TRACE, PAIR>(&bars->ebar[0], par_prev, 201, L, (int)c.layer_ctr);
+                                  wait_ev<TRACE, PAIR>(&bars->ebar[1], par_prev, 202, L, (int)c.layer_ctr);
+                                  c.ph_e_other += PH_CLK() - p0; }
                 } else if (!is_pe) {
-                    if (i == 0) wait_or_report<TRACE>(&bars->ebar[0], par_prev, 201, L, (int)c.layer_ctr);
-                    if (i == KB_PER_HALF_PREV) wait_or_report<TRACE>(&bars->ebar[1], par_prev, 202, L, (int)c.layer_ctr);
+                    if (i == 0) { const long long p0 = PH_CLK(); wait_ev<TRACE, PAIR>(&bars->ebar[0], par_prev, 201, L, (int)c.layer_ctr);
+                                  if (L == 1) c.ph_e0 += PH_CLK() - p0; else c.ph_e_other += PH_CLK() - p0; }
+                    if (i == KB_PER_HALF_PREV) { const long long p0 = PH_CLK(); wait_ev<TRACE, PAIR>(&bars->ebar[1], par_prev, 202, L, (int)c.layer_ctr);
+                                                 if (L == 1) c.ph_e1 += PH_CLK() - p0; else c.ph_e_other += PH_CLK() - p0; }
                 }
             }
             if constexpr (TRACE) { const long long c1 = clock64(); c.t_e += c1 - c0; c.t_e_layer[c.layer_ctr % 11] += c1 - c0; c0 = c1; }
-            if (L == 0 && h == 0 && i == 0) wait_or_report<TRACE>(&bars->pe_ready, c.iter_ctr & 1, 203, L, (int)c.iter_ctr);
+            if (L == 0 && h == 0 && i == 0) wait_ev<TRACE, PAIR>(&bars->pe_ready, c.iter_ctr & 1, 203, L, (int)c.iter_ctr);
             if constexpr (TRACE) { const long long c1 = clock64(); c.t_pe += c1 - c0; c0 = c1; }
-            if (!(ABL & 2) || (c.layer_ctr == 0 && L == 0 && h * CNT + i < NSTAGE))
+            if (!(ABL & 2) || (c.layer_ctr == 0 && L == 0 && h * CNT + i < NSTAGE)) {
+                const long long p0 = PH_CLK();
                 wait_or_report<TRACE>(&bars->wfull[c.stage], c.wpar, 204, L, (int)c.stage);
+                if constexpr (PAIR) mbar_wait_cluster(&bars->pfull[c.stage], c.wpar);
+                c.ph_w += PH_CLK() - p0;
+            }
             if constexpr (TRACE) c.t_w += clock64() - c0;
-            if (i == 0) wait_or_report<TRACE>(&bars->bfull[c.bslot], c.bpar, 205, L, (int)c.bslot);
+            if (i == 0) {
+                wait_or_report<TRACE>(&bars->bfull[c.bslot], c.bpar, 205, L, (int)c.bslot);
+                if constexpr (PAIR) mbar_wait_cluster(&bars->pbfull[c.bslot], c.bpar);
+            }
             tc_fence_after();
             if (elect_one()) {
                 if (i == 0) {
@@ -259,8 +317,8 @@ __device__ __forceinline__ void issue_layer(IssueCtx& c) {
                     // this MMA overwrites the accumulator, every weight MMA below accumulates
 #pragma unroll
                     for (int slot = 0; slot < 2; ++slot)
-                        umma_bf16_lohi(c.tmem_base + slot * 256 + h * NH, c.ones_lo, c.bt_lo + c.bslot * (4096 >> 4), HI_NOSWZ, IDESC, 0u);
-                    umma_commit(&bars->bempty[c.bslot]);
+                        umma_any<PAIR>(c.tmem_base + slot * 256 + h * NH, c.ones_lo, c.bt_lo + c.bslot * (4096 >> 4), HI_NOSWZ, IDESC, 0u);
+                    commit_any<PAIR>(&bars->bempty[c.bslot]);
                 }
                 const uint32_t b_lo = c.w_lo + c.stage * (STAGE_BYTES >> 4);
 #pragma unroll
@@ -268,14 +326,14 @@ __device__ __forceinline__ void issue_layer(IssueCtx& c) {
                     const uint32_t a_lo = is_pe ? c.pe_lo + slot * (16384 >> 4) : c.a_lo + slot * (65536 >> 4) + i * (16384 >> 4);
                     const uint32_t d = c.tmem_base + slot * 256 + h * NH;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, a_lo + 2 * k, b_lo + 2 * k, c.hi, IDESC, 1u);
+                    for (int k = 0; k < 4; ++k) umma_any<PAIR>(d, a_lo + 2 * k, b_lo + 2 * k, c.hi, IDESC, 1u);
                 }
-                umma_commit(&bars->wempty[c.stage]);
+                commit_any<PAIR>(&bars->wempty[c.stage]);
                 const bool last = (i == CNT - 1);
-                if (h == 0 && last) umma_commit(&bars->cbar[0]);
-                if (h == 1 && (N_FIRST > 0 ? i == N_FIRST - 1 : last)) umma_commit(&bars->cbar[1]);
-                if (h == 1 && last) umma_commit(&bars->cbar[2]);
-                if (h == 1 && last && L == 5) umma_commit(&bars->pe_free);
+                if (h == 0 && last) commit_any<PAIR>(&bars->cbar[0]);
+                if (h == 1 && (N_FIRST > 0 ? i == N_FIRST - 1 : last)) commit_any<PAIR>(&bars->cbar[1]);
+                if (h == 1 && last) commit_any<PAIR>(&bars->cbar[2]);
+                if (h == 1 && last && L == 5) commit_any<PAIR>(&bars->pe_free);
             }
             __syncwarp();
             if (i == 0) { c.bslot ^= 1; if (c.bslot == 0) c.bpar ^= 1; }
@@ -298,8 +356,19 @@ __device__ int g_save_abl;      // profiling builds: switch parts of the activat
 #define SAVE_OFF(bit) false
 #endif
 
-template <bool TRACE, int ABL = 0, bool SAVE = false>
+// PAIR = true (inference build): the kernel runs as clusters of two CTAs.  Every MMA is ONE tcgen05.mma.cta_group::2 over the 2 x 128
+// rows of the pair (issued by the leader's warp 1), and the B operand -- the weight stage -- is split across the pair: each CTA streams
+// and keeps only HALF of the rows of every stage.  Why: the N = 128 MMAs of the single-CTA form read 8 KB of operands per 64 cycles,
+// all 128 B/clk of an SM's shared memory, so the epilogue's activation stores (128 KB per layer) and the weight ring's refills compete
+// with the tensor pipe for the same port -- a layer measured 5.2 kcycles against 4.35 of MMA time (profiles/r03_phase_timers.txt), and
+// total shared-memory traffic / 128 B/clk reproduces the iteration time.  A pair reads 6 KB per MMA per CTA and writes half the weight
+// bytes.  Schedule, layouts, packed blob and epilogue are the single-CTA kernel's: a pair iteration is two 256-point chunks, CTA r takes
+// chunk 2 it + r.  Cross-CTA protocol: commits are multicast to both CTAs' barriers; the peer's epilogue / positional-encoding warps
+// arrive remotely on the LEADER's event barriers; the peer's (otherwise idle) warp 1 relays "my half of the stage has landed".
+template <bool TRACE, int ABL = 0, bool SAVE = false, bool PAIR = false>
 __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, int n_steps, int n_rays, float* __restrict__ trace) {
+    constexpr int NSTAGE = RingOf<PAIR>::N, STAGE_BYTES = RingOf<PAIR>::BYTES;
+    static_assert(!(PAIR && (TRACE || SAVE || ABL != 0)), "the pair build is the plain inference kernel");
     // Dynamic shared memory is the only shared allocation of this kernel, so it starts at offset 0 of the CTA's
     // window: 1024-byte aligned as the 128B-swizzle atoms need.  (No pointer re-alignment arithmetic here: it would
     // make the compiler lose the shared address space and emit generic LD/ST for every epilogue access.)
@@ -312,7 +381,12 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
     float* s_dirb = reinterpret_cast<float*>(sm + OFF_DIRB);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long n_iter = (a.P + 255) / 256;
+    // iteration space: single CTA: chunk = it, one chunk of 256 points per CTA iteration; pair: chunk = 2 it + rank
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const long long n_iter = PAIR ? (a.P + 511) / 512 : (a.P + 255) / 256;
+    const long long it_first = PAIR ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+    const long long it_step = PAIR ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
+#define CHUNK_OF(it_) (PAIR ? 2 * (it_) + (long long)rank : (it_))
 
     // ---- one-time setup -------------------------------------------------------------------
     if (tid < 4) s_sb[tid] = a.cond[8 * 256 + 3 * 128 + tid];
@@ -322,22 +396,27 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
     for (int i = tid; i < 256; i += NTHREADS_BF16) s_aw[i] = a.w[P_ALPHA_W][i];
     for (int i = tid; i < 384; i += NTHREADS_BF16) s_rw[i] = a.w[P_RGB_W][i];
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars->wfull[s], 1); mbar_init(&bars->wempty[s], 1); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars->wfull[s], 1); mbar_init(&bars->wempty[s], 1); mbar_init(&bars->pfull[s], 1); }
         for (int j = 0; j < 3; ++j) mbar_init(&bars->cbar[j], 1);
-        for (int j = 0; j < 2; ++j) mbar_init(&bars->ebar[j], N_EPI / 32);
-        mbar_init(&bars->pe_ready, N_PE);
+        for (int j = 0; j < 2; ++j) mbar_init(&bars->ebar[j], PAIR ? 2 * (N_EPI / 32) : N_EPI / 32);
+        mbar_init(&bars->pe_ready, PAIR ? 2 * (N_PE / 32) : N_PE);
         mbar_init(&bars->pe_free, 1);
         mbar_init(&bars->dirb_ready, N_PE);
         mbar_init(&bars->dirb_free, N_EPI / 32);
-        for (int j = 0; j < 2; ++j) { mbar_init(&bars->bfull[j], 1); mbar_init(&bars->bempty[j], 1); }
+        for (int j = 0; j < 2; ++j) { mbar_init(&bars->bfull[j], 1); mbar_init(&bars->bempty[j], 1); mbar_init(&bars->pbfull[j], 1); }
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(&bars->tmem_base, 512);
-        tmem_relinquish();
+        if constexpr (PAIR) {
+            tmem_alloc_pair(&bars->tmem_base, 512);
+        } else {
+            tmem_alloc(&bars->tmem_base, 512);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();      // both CTAs' barriers and tensor memory exist before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
@@ -347,13 +426,16 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
             const uint8_t* blob = reinterpret_cast<const uint8_t*>(a.packed);
             const uint8_t* tiles = reinterpret_cast<const uint8_t*>(a.cond + 2436);
             uint32_t g = 0, bh = 0;
-            for (long long it = blockIdx.x; it < n_iter; it += gridDim.x) {
+            // pair build: this CTA's HALF of the rows of every stage / bias tile (rows [rank * NH / 2, (rank + 1) * NH / 2) are the first /
+            // second half of the image's bytes: 8-row groups are contiguous)
+            constexpr uint32_t SPLIT = PAIR ? 2u : 1u;
+            for (long long it = it_first; it < n_iter; it += it_step) {
                 for (int s = 0; s < n_steps; ++s, ++g) {
                     const uint32_t stage = g % NSTAGE, round = g / NSTAGE;
                     if (c_steps[s].first) {            // first step of a (layer, half): its bias tile
                         const uint32_t slot = bh & 1, l = c_steps[s].layer, h = c_steps[s].acc_col ? 1u : 0u;
-                        const uint32_t bytes = (uint32_t)c_steps[s].n8 * 8u * 32u;
-                        const uint32_t off = l < 8 ? (2 * l + h) * 4096u : 65536u + (2 * (l - 8) + h) * 2048u;
+                        const uint32_t bytes = (uint32_t)c_steps[s].n8 * 8u * 32u / SPLIT;
+                        const uint32_t off = (l < 8 ? (2 * l + h) * 4096u : 65536u + (2 * (l - 8) + h) * 2048u) + rank * bytes;
                         wait_or_report<TRACE>(&bars->bempty[slot], ((bh >> 1) & 1) ^ 1, 102, s, (int)bh);
                         mbar_arrive_expect_tx(&bars->bfull[slot], bytes);
                         bulk_g2s(sm + OFF_BT + slot * 4096, tiles + off, bytes, &bars->bfull[slot]);
@@ -361,11 +443,26 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                     }
                     if ((ABL & 2) && g >= NSTAGE) continue;
                     wait_or_report<TRACE>(&bars->wempty[stage], (round & 1) ^ 1, 101, s, (int)g);
-                    const uint32_t bytes = (uint32_t)c_steps[s].n8 * 8u * 128u;
+                    const uint32_t bytes = (uint32_t)c_steps[s].n8 * 8u * 128u / SPLIT;
                     mbar_arrive_expect_tx(&bars->wfull[stage], bytes);
-                    bulk_g2s(sm + OFF_W + stage * STAGE_BYTES, blob + c_steps[s].offset, bytes, &bars->wfull[stage]);
+                    bulk_g2s(sm + OFF_W + stage * STAGE_BYTES, blob + c_steps[s].offset + rank * bytes, bytes, &bars->wfull[stage]);
                 }
             }
+        }
+    } else if (warp == 1 && PAIR && rank != 0) {
+        // ================= relay (peer CTA of a pair): tell the leader when MY half of a bias tile / weight stage has landed =========
+        if (lane == 0) {
+            uint32_t g = 0, bh = 0;
+            for (long long it = it_first; it < n_iter; it += it_step)
+                for (int s = 0; s < n_steps; ++s, ++g) {
+                    if (c_steps[s].first) {
+                        mbar_wait(&bars->bfull[bh & 1], (bh >> 1) & 1);
+                        mbar_arrive_remote(&bars->pbfull[bh & 1], 0);
+                        ++bh;
+                    }
+                    mbar_wait(&bars->wfull[g % NSTAGE], (g / NSTAGE) & 1);
+                    mbar_arrive_remote(&bars->pfull[g % NSTAGE], 0);
+                }
         }
     } else if (warp == 1) {
         // ================= MMA issuer (whole warp converged; one elected lane issues) ==========
@@ -381,23 +478,31 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
         c.bslot = 0; c.bpar = 0;
         c.stage = 0; c.wpar = 0; c.layer_ctr = 0; c.iter_ctr = 0;
         c.t_e = c.t_w = c.t_pe = 0;
+        c.ph_e0 = c.ph_e1 = c.ph_e_other = c.ph_w = 0;
+        const long long ph_t0 = PH_CLK();
         for (int j = 0; j < 11; ++j) c.t_e_layer[j] = 0;
         const long long t_tot = clock64();
-        for (long long it = blockIdx.x; it < n_iter; it += gridDim.x, ++c.iter_ctr) {
+        for (long long it = it_first; it < n_iter; it += it_step, ++c.iter_ctr) {
             // Layers of equal geometry share ONE copy of the straight-line issue code (L1-L4, L6, L7 are 256 x 256 after a 256-wide
             // layer; V1, V2 are 128 x 128 after a 128-wide one): 11 inlined copies were 78 KB of SASS streamed once per iteration, which
             // together with the epilogue and PE code overflowed the instruction cache the epilogue warps live in (ncu: stall_no_inst).
-            issue_layer<0, TRACE, ABL>(c);
+            issue_layer<0, TRACE, ABL, PAIR>(c);
 #pragma unroll 1
             for (int seg = 0; seg < 2; ++seg) {
 #pragma unroll 1
-                for (int r = 0; r < (seg ? 2 : 4); ++r) issue_layer<1, TRACE, ABL>(c);
-                if (seg == 0) issue_layer<5, TRACE, ABL>(c);
+                for (int r = 0; r < (seg ? 2 : 4); ++r) issue_layer<1, TRACE, ABL, PAIR>(c);
+                if (seg == 0) issue_layer<5, TRACE, ABL, PAIR>(c);
             }
-            issue_layer<8, TRACE, ABL>(c);
+            issue_layer<8, TRACE, ABL, PAIR>(c);
 #pragma unroll 1
-            for (int r = 0; r < 2; ++r) issue_layer<9, TRACE, ABL>(c);
+            for (int r = 0; r < 2; ++r) issue_layer<9, TRACE, ABL, PAIR>(c);
         }
+#ifdef INERF_PHASE_TIMERS
+        if (lane == 0) {
+            unsigned long long* g = g_phase[blockIdx.x];
+            g[0] = (unsigned long long)(PH_CLK() - ph_t0); g[1] = c.iter_ctr; g[2] = c.ph_e0; g[3] = c.ph_e1; g[4] = c.ph_e_other; g[5] = c.ph_w;
+        }
+#endif
         if constexpr (TRACE) {      // per-CTA issuer timing after the activation trace: {total, wait E, wait PE, wait weights, iterations}
             if (lane == 0) {
                 float* t = trace + (size_t)11 * 256 * 256 + blockIdx.x * 8;
@@ -416,8 +521,10 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
         const uint32_t rsw = row & 7;
         uint32_t layer_ctr = 0, iter_ctr = 0;
         long long te_wait = 0, te_ld = 0, te_c1 = 0, te_st = 0;       // trace build: epilogue phase cycles (warp 4)
-        for (long long it = blockIdx.x; it < n_iter; it += gridDim.x, ++iter_ctr) {
-            const long long p0 = it * 256 + slot * 128;
+        long long ph_wait[2] = {0, 0}, ph_dur[2] = {0, 0}, ph_c1 = 0;  // INERF_PHASE_TIMERS build: L1..L7, per half: wait for the commit / work until the arrival; wait for C1
+        for (long long it = it_first; it < n_iter; it += it_step, ++iter_ctr) {
+            const long long chunk = CHUNK_OF(it);
+            const long long p0 = chunk * 256 + slot * 128;
             long long p = p0 + row;
             const bool in_range = p < a.P;
             if (!in_range) p = a.P - 1;
@@ -432,9 +539,11 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                 for (int h = 0; h < 2; ++h) {
                     long long q0 = 0;
                     if constexpr (TRACE) q0 = clock64();
+                    const long long ph0 = PH_CLK();
                     wait_or_report<TRACE>(&bars->cbar[h == 0 ? 0 : 2], par, 302 + h, l, (int)layer_ctr);
                     __syncwarp();
                     tc_fence_after();
+                    const long long ph1 = PH_CLK();
                     if constexpr (TRACE) { const long long q1 = clock64(); te_wait += q1 - q0; q0 = q1; }
                     uint32_t packed[64];
                     const int nchunk = NH >> 5;      // 4 (N=256) or 2 (N=128)
@@ -457,7 +566,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                             const int f0 = h * NH + c * 32;                 // first output feature of the chunk
                             uint32_t neg = 0;
                             float* tr = TRACE ? trace + ((size_t)l * 256 + slot * 128 + row) * 256 + f0 : nullptr;
-                            const bool dump = TRACE && it == 0;
+                            const bool dump = TRACE && chunk == 0;
                             switch (l) {                                    // layer kind is warp-uniform: one specialised body per chunk
                                 case 7: epi_convert<1, TRACE, SAVE>(r, &packed[c * 16], nullptr, s_aw + f0, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump, neg); break;
                                 case 8: epi_convert<2, TRACE, SAVE>(r, &packed[c * 16], s_dirb + (slot * RMAX + ray_local) * 128 + f0, nullptr, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump, neg); break;
@@ -465,7 +574,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                                 default: epi_convert<0, TRACE, SAVE>(r, &packed[c * 16], nullptr, nullptr, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump, neg); break;
                             }
                             if (SAVE && !SAVE_OFF(1))      // training: the ReLU mask word of the chunk (the activations follow as a bulk copy of the smem image)
-                                a.save_mask[(((size_t)it * 2 + slot) * TRAIN_MASK_WORDS + train_mask_of(l) + (f0 >> 5)) * 128 + row] = ~neg;
+                                a.save_mask[(((size_t)chunk * 2 + slot) * TRAIN_MASK_WORDS + train_mask_of(l) + (f0 >> 5)) * 128 + row] = ~neg;
                             if (!SAVE && h == 1 && l != 10) {
                                 // second half: nothing reads these K-blocks any more (its own MMAs are complete), so each chunk goes to shared
                                 // memory as soon as it is converted and drains behind the next chunk's load instead of in front of the fence
@@ -481,7 +590,9 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                     tc_fence_before();
                     if constexpr (TRACE) { const long long q1 = clock64(); te_ld += q1 - q0; q0 = q1; }
                     if (l != 10 || SAVE) {
+                        const long long ph2 = PH_CLK();
                         if (h == 0) wait_or_report<TRACE>(&bars->cbar[1], par, 304, l, (int)layer_ctr);
+                        ph_c1 += PH_CLK() - ph2;
                         if constexpr (SAVE) {
                             // training: each warp bulk-copies its own 32 rows of the K-blocks it writes (4 KB per K-block image) to HBM, so no
                             // barrier couples the warps.  Before overwriting them, lane 0 waits until the copy that last read these rows has
@@ -511,7 +622,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                             if (lane == 0 && !SAVE_OFF(2)) {
                                 const int kb0 = (h * NH) >> 6, nkb = NH >> 6;      // 2 K-blocks per half (N = 256) or 1 (N = 128)
                                 const uint32_t wrow = (uint32_t)(warp & 3) * 4096u;      // 32 rows = 4 row groups of 1 KB
-                                uint8_t* g = a.save_img + (((size_t)it * 2 + slot) * TRAIN_IMGS + train_img_of(l) + kb0) * 16384 + wrow;
+                                uint8_t* g = a.save_img + (((size_t)chunk * 2 + slot) * TRAIN_IMGS + train_img_of(l) + kb0) * 16384 + wrow;
                                 for (int k = 0; k < nkb; ++k) bulk_s2g(g + k * 16384, act + (kb0 + k) * 16384 + wrow, 4096u);
                                 bulk_commit();
                             }
@@ -520,7 +631,8 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                     // one arrival per warp: 256 per-thread arrivals on one mbarrier serialise in the shared-memory pipe and sit on
                     // the layer-to-layer critical path (E1 gates the next layer's third K-block)
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars->ebar[h]);
+                    if (lane == 0) { if constexpr (PAIR) mbar_arrive_remote(&bars->ebar[h], 0); else mbar_arrive(&bars->ebar[h]); }
+                    if (l >= 1 && l <= 7) { const long long ph3 = PH_CLK(); ph_wait[h] += ph1 - ph0; ph_dur[h] += ph3 - ph1; }
                     if constexpr (TRACE) te_st += clock64() - q0;
                 }
                 if (l == 8) {
@@ -540,6 +652,12 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
         if constexpr (SAVE) {
             if (lane == 0) bulk_wait_all();
         }
+#ifdef INERF_PHASE_TIMERS
+        if ((warp == 4 || warp == 11) && lane == 0) {
+            unsigned long long* g = g_phase[blockIdx.x] + (warp == 4 ? 6 : 11);
+            g[0] = ph_wait[0]; g[1] = ph_dur[0]; g[2] = ph_wait[1]; g[3] = ph_dur[1]; g[4] = ph_c1;
+        }
+#endif
         if constexpr (TRACE) {
             if (warp == 4 && lane == 0) {
                 float* t = trace + (size_t)11 * 256 * 256 + (148 + blockIdx.x) * 8;
@@ -556,12 +674,13 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
             for (int j = 0; j < 27; ++j) wdir[j] = wrow[j];
         }
         uint32_t iter_ctr = 0;
-        for (long long it = blockIdx.x; it < n_iter; it += gridDim.x, ++iter_ctr) {
+        for (long long it = it_first; it < n_iter; it += it_step, ++iter_ctr) {
+            const long long chunk = CHUNK_OF(it);
             // ---- gamma_10(o + d z) for row t of both slots ---------------------------------------
             uint32_t pk[2][32];
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl) {
-                long long p = it * 256 + sl * 128 + t;
+                long long p = chunk * 256 + sl * 128 + t;
                 if (p > a.P - 1) p = a.P - 1;
                 const long long ray = p / a.s;
                 const float* r = a.rays + ray * a.ray_stride;
@@ -601,11 +720,16 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                         make_uint4(pk[sl][4 * q], pk[sl][4 * q + 1], pk[sl][4 * q + 2], pk[sl][4 * q + 3]);
             }
             fence_proxy_async_smem();
-            mbar_arrive(&bars->pe_ready);
+            if constexpr (PAIR) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(&bars->pe_ready, 0);
+            } else {
+                mbar_arrive(&bars->pe_ready);
+            }
             if (SAVE && !SAVE_OFF(4)) {          // training: gamma(p) is the X operand of dW for pts_linears.0 / .5
 #pragma unroll
                 for (int sl = 0; sl < 2; ++sl) {
-                    uint8_t* dst = a.save_img + (((size_t)it * 2 + sl) * TRAIN_IMGS + TRAIN_IMG_PE) * 16384 + (t >> 3) * 1024 + (t & 7) * 128;
+                    uint8_t* dst = a.save_img + (((size_t)chunk * 2 + sl) * TRAIN_IMGS + TRAIN_IMG_PE) * 16384 + (t >> 3) * 1024 + (t & 7) * 128;
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                         *reinterpret_cast<uint4*>(dst + ((q ^ (t & 7)) << 4)) =
@@ -618,7 +742,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                 const int q = lane;
                 if (q < 2 * RMAX) {
                     const int sl = q / RMAX, rl = q - sl * RMAX;
-                    long long pfirst = it * 256 + sl * 128;
+                    long long pfirst = chunk * 256 + sl * 128;
                     if (pfirst > a.P - 1) pfirst = a.P - 1;
                     long long ray = pfirst / a.s + rl;
                     if (ray > n_rays - 1) ray = n_rays - 1;
@@ -640,7 +764,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                 if (SAVE && !SAVE_OFF(4)) {      // training: gamma(v) per POINT, the X operand of dW for the view columns of views_linears.0
 #pragma unroll
                     for (int sl = 0; sl < 2; ++sl) {
-                        long long p = it * 256 + sl * 128 + t, pfirst = it * 256 + sl * 128;
+                        long long p = chunk * 256 + sl * 128 + t, pfirst = chunk * 256 + sl * 128;
                         if (p > a.P - 1) p = a.P - 1;
                         if (pfirst > a.P - 1) pfirst = a.P - 1;
                         const int src = sl * RMAX + (int)(p / a.s - pfirst / a.s);
@@ -648,7 +772,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
 #pragma unroll
                         for (int j = 0; j < 27; ++j) g[j] = __shfl_sync(0xffffffffu, enc[j], src);
                         g[27] = 0.f;
-                        uint8_t* dst = a.save_img + (((size_t)it * 2 + sl) * TRAIN_IMGS + TRAIN_IMG_DIR) * 16384 + (t >> 3) * 1024 + (t & 7) * 128;
+                        uint8_t* dst = a.save_img + (((size_t)chunk * 2 + sl) * TRAIN_IMGS + TRAIN_IMG_DIR) * 16384 + (t >> 3) * 1024 + (t & 7) * 128;
 #pragma unroll
                         for (int qq = 0; qq < 8; ++qq) {
                             uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -676,7 +800,13 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
     // ---- teardown ---------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if constexpr (PAIR) {
+        cluster_sync_all();      // nobody leaves while the peer may still arrive on / multicast to this CTA
+        if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
+    } else {
+        if (warp == 2) tmem_dealloc(tmem_base, 512);
+    }
+#undef CHUNK_OF
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -800,6 +930,15 @@ void mlp_bf16_stage_offsets(uint32_t (*off)[2][5]) {
     }
 }
 
+#ifdef INERF_PHASE_TIMERS
+}  // namespace inerf
+// profiling builds only (not part of include/inerf_b200.h): the phase timers of the last launch, [148][16] uint64
+extern "C" int inerf_debug_phase_timers(unsigned long long* out_host) {
+    return (int)cudaMemcpyFromSymbol(out_host, g_phase, sizeof(unsigned long long) * 148 * 16);
+}
+namespace inerf {
+#endif
+
 static int* g_hang_host = nullptr;
 
 int mlp_bf16_hang_info(int32_t* out8) {
@@ -870,8 +1009,36 @@ int mlp_bf16_launch(const MlpArgs& a, bool embedded, cudaStream_t st) {
         mlp_bf16_kernel<false, 0, true><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, nullptr);
         return check_launch("inerf_mlp_fwd_train[bf16]");
     }
-    if (a.trace) mlp_bf16_kernel<true><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, a.trace);
-    else mlp_bf16_kernel<false><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, nullptr);
+    if (a.trace) {
+        mlp_bf16_kernel<true><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, a.trace);
+        return check_launch("inerf_mlp_fwd[bf16]");
+    }
+    // inference: the CTA-pair build (clusters of two; INERF_MLP_PAIR=0, read once, keeps the single-CTA kernel for A/B runs)
+    static const bool use_pair = [] { const char* e = getenv("INERF_MLP_PAIR"); return !e || atoi(e) != 0; }();
+    if (use_pair && num_sms() >= 2) {
+        static thread_local int pair_dev = -1;
+        if (pair_dev != dev) {
+            cudaError_t e = cudaFuncSetAttribute(mlp_bf16_kernel<false, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+            if (e != cudaSuccess) { set_error("mlp_bf16: setup: %s", cudaGetErrorString(e)); return (int)e; }
+            pair_dev = dev;
+        }
+        const long long n_pair_iter = (a.P + 511) / 512;
+        const long long max_pairs = num_sms() / 2;
+        const long long pairs = n_pair_iter < max_pairs ? n_pair_iter : max_pairs;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(2 * pairs));
+        cfg.blockDim = dim3(NTHREADS_BF16);
+        cfg.dynamicSmemBytes = SMEM_ALLOC;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_bf16_kernel<false, 0, false, true>, a, S.n_steps, n_rays, (float*)nullptr);
+        if (e != cudaSuccess) { set_error("inerf_mlp_fwd[bf16 pair]: %s", cudaGetErrorString(e)); return (int)e; }
+        return check_launch("inerf_mlp_fwd[bf16 pair]");
+    }
+    mlp_bf16_kernel<false><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, nullptr);
     return check_launch("inerf_mlp_fwd[bf16]");
 }
 

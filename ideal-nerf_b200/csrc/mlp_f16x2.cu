@@ -266,11 +266,11 @@ __device__ __forceinline__ void epi16(const uint32_t (&r)[16], const uint32_t (&
         }
         if constexpr (KIND == 1) {
             const float4 w = *reinterpret_cast<const float4*>(aw + j);
-            alpha = fmaf(fmaxf(v[0], 0.f), w.x, alpha); alpha = fmaf(fmaxf(v[1], 0.f), w.y, alpha);
-            alpha = fmaf(fmaxf(v[2], 0.f), w.z, alpha); alpha = fmaf(fmaxf(v[3], 0.f), w.w, alpha);
+            alpha = fmaf(relu_nan(v[0]), w.x, alpha); alpha = fmaf(relu_nan(v[1]), w.y, alpha);
+            alpha = fmaf(relu_nan(v[2]), w.z, alpha); alpha = fmaf(relu_nan(v[3]), w.w, alpha);
         }
         if constexpr (KIND == 3) {
-            const float q[4] = {fmaxf(v[0], 0.f), fmaxf(v[1], 0.f), fmaxf(v[2], 0.f), fmaxf(v[3], 0.f)};
+            const float q[4] = {relu_nan(v[0]), relu_nan(v[1]), relu_nan(v[2]), relu_nan(v[3])};
             const float4 w0 = *reinterpret_cast<const float4*>(rw + j);
             const float4 w1 = *reinterpret_cast<const float4*>(rw + 128 + j);
             const float4 w2 = *reinterpret_cast<const float4*>(rw + 256 + j);
