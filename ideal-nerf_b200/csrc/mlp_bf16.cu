@@ -368,7 +368,7 @@ __device__ int g_save_abl;      // profiling builds: switch parts of the activat
 template <bool TRACE, int ABL = 0, bool SAVE = false, bool PAIR = false>
 __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, int n_steps, int n_rays, float* __restrict__ trace) {
     constexpr int NSTAGE = RingOf<PAIR>::N, STAGE_BYTES = RingOf<PAIR>::BYTES;
-    static_assert(!(PAIR && (TRACE || SAVE || ABL != 0)), "the pair build is the plain inference kernel");
+    static_assert(!(PAIR && (TRACE || ABL != 0)), "the pair build has no trace / ablation variants");
     // Dynamic shared memory is the only shared allocation of this kernel, so it starts at offset 0 of the CTA's
     // window: 1024-byte aligned as the 128B-swizzle atoms need.  (No pointer re-alignment arithmetic here: it would
     // make the compiler lose the shared address space and emit generic LD/ST for every epilogue access.)
@@ -524,6 +524,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
         long long ph_wait[2] = {0, 0}, ph_dur[2] = {0, 0}, ph_c1 = 0;  // INERF_PHASE_TIMERS build: L1..L7, per half: wait for the commit / work until the arrival; wait for C1
         for (long long it = it_first; it < n_iter; it += it_step, ++iter_ctr) {
             const long long chunk = CHUNK_OF(it);
+            const bool chunk_ok = !PAIR || chunk * 256 < a.P;      // pair build: the peer's last chunk may lie wholly past the end (nothing is saved for it)
             const long long p0 = chunk * 256 + slot * 128;
             long long p = p0 + row;
             const bool in_range = p < a.P;
@@ -573,7 +574,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                                 case 10: epi_convert<3, TRACE, SAVE>(r, &packed[c * 16], nullptr, nullptr, s_rw + f0, alpha, rgb0, rgb1, rgb2, tr, dump, neg); break;
                                 default: epi_convert<0, TRACE, SAVE>(r, &packed[c * 16], nullptr, nullptr, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump, neg); break;
                             }
-                            if (SAVE && !SAVE_OFF(1))      // training: the ReLU mask word of the chunk (the activations follow as a bulk copy of the smem image)
+                            if (SAVE && !SAVE_OFF(1) && chunk_ok)      // training: the ReLU mask word of the chunk (the activations follow as a bulk copy of the smem image)
                                 a.save_mask[(((size_t)chunk * 2 + slot) * TRAIN_MASK_WORDS + train_mask_of(l) + (f0 >> 5)) * 128 + row] = ~neg;
                             if (!SAVE && h == 1 && l != 10) {
                                 // second half: nothing reads these K-blocks any more (its own MMAs are complete), so each chunk goes to shared
@@ -598,7 +599,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                             // barrier couples the warps.  Before overwriting them, lane 0 waits until the copy that last read these rows has
                             // left shared memory: that is two copies back (this half's K-blocks were written by the same half of the previous
                             // layer) unless the layer widens (l == 0 after the 128-wide rgb layer), where it is the latest one.
-                            if (lane == 0) { if (h == 0 && l == 0) bulk_wait_read_all(); else bulk_wait_read_but_one(); }
+                            if (lane == 0 && !SAVE_OFF(8)) { if (h == 0 && l == 0) bulk_wait_read_all(); else bulk_wait_read_but_one(); }
                         }
                         __syncwarp();      // h1 has finished reading the K-blocks written below
                         if constexpr (TRACE) { const long long q1 = clock64(); te_c1 += q1 - q0; q0 = q1; }
@@ -619,7 +620,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                         fence_proxy_async_smem();
                         if constexpr (SAVE) {
                             __syncwarp();
-                            if (lane == 0 && !SAVE_OFF(2)) {
+                            if (lane == 0 && !SAVE_OFF(2) && chunk_ok) {
                                 const int kb0 = (h * NH) >> 6, nkb = NH >> 6;      // 2 K-blocks per half (N = 256) or 1 (N = 128)
                                 const uint32_t wrow = (uint32_t)(warp & 3) * 4096u;      // 32 rows = 4 row groups of 1 KB
                                 uint8_t* g = a.save_img + (((size_t)chunk * 2 + slot) * TRAIN_IMGS + train_img_of(l) + kb0) * 16384 + wrow;
@@ -726,7 +727,8 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
             } else {
                 mbar_arrive(&bars->pe_ready);
             }
-            if (SAVE && !SAVE_OFF(4)) {          // training: gamma(p) is the X operand of dW for pts_linears.0 / .5
+            const bool chunk_ok = !PAIR || chunk * 256 < a.P;
+            if (SAVE && !SAVE_OFF(4) && chunk_ok) {          // training: gamma(p) is the X operand of dW for pts_linears.0 / .5
 #pragma unroll
                 for (int sl = 0; sl < 2; ++sl) {
                     uint8_t* dst = a.save_img + (((size_t)chunk * 2 + sl) * TRAIN_IMGS + TRAIN_IMG_PE) * 16384 + (t >> 3) * 1024 + (t & 7) * 128;
@@ -761,7 +763,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
 #pragma unroll
                     for (int j = 0; j < 27; ++j) enc[j] = 0.f;
                 }
-                if (SAVE && !SAVE_OFF(4)) {      // training: gamma(v) per POINT, the X operand of dW for the view columns of views_linears.0
+                if (SAVE && !SAVE_OFF(4) && chunk_ok) {      // training: gamma(v) per POINT, the X operand of dW for the view columns of views_linears.0
 #pragma unroll
                     for (int sl = 0; sl < 2; ++sl) {
                         long long p = chunk * 256 + sl * 128 + t, pfirst = chunk * 256 + sl * 128;
@@ -946,6 +948,31 @@ int mlp_bf16_hang_info(int32_t* out8) {
     return INERF_OK;
 }
 
+template <bool SAVE>
+static int launch_pair(const MlpArgs& a, int n_steps, int n_rays, int dev, cudaStream_t st) {
+    static thread_local int pair_dev = -1;
+    if (pair_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_bf16_kernel<false, 0, SAVE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+        if (e != cudaSuccess) { set_error("mlp_bf16: setup: %s", cudaGetErrorString(e)); return (int)e; }
+        pair_dev = dev;
+    }
+    const long long n_pair_iter = (a.P + 511) / 512;
+    const long long max_pairs = num_sms() / 2;
+    const long long pairs = n_pair_iter < max_pairs ? n_pair_iter : max_pairs;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(NTHREADS_BF16);
+    cfg.dynamicSmemBytes = SMEM_ALLOC;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_bf16_kernel<false, 0, SAVE, true>, a, n_steps, n_rays, (float*)nullptr);
+    if (e != cudaSuccess) { set_error("inerf_mlp_fwd[bf16 pair]: %s", cudaGetErrorString(e)); return (int)e; }
+    return check_launch(SAVE ? "inerf_mlp_fwd_train[bf16 pair]" : "inerf_mlp_fwd[bf16 pair]");
+}
+
 int mlp_bf16_launch(const MlpArgs& a, bool embedded, cudaStream_t st) {
     if (embedded)
         return fail(INERF_E_UNSUPPORTED, "bf16 mode is built for the fused (rays, z) entry; FaceNeRF.forward on embedded rows runs in fp32 mode");
@@ -966,6 +993,10 @@ int mlp_bf16_launch(const MlpArgs& a, bool embedded, cudaStream_t st) {
     const long long n_iter = (a.P + 255) / 256;
     const int grid = (int)(n_iter < (long long)num_sms() ? n_iter : (long long)num_sms());
     const int n_rays = (int)(a.P / a.s);
+    // the CTA-pair build (clusters of two) runs the inference and the activation-saving forward; INERF_MLP_PAIR=0 (read once) keeps the
+    // single-CTA kernels for A/B runs, which also serve the trace / ablation builds
+    static const bool pair_env = [] { const char* e = getenv("INERF_MLP_PAIR"); return !e || atoi(e) != 0; }();
+    const bool use_pair = pair_env && num_sms() >= 2 && !a.trace;
     if (a.trace) {
         if (!g_hang_host) {
             int* dptr = nullptr;
@@ -1006,6 +1037,7 @@ int mlp_bf16_launch(const MlpArgs& a, bool embedded, cudaStream_t st) {
             }
         }
 #endif
+        if (use_pair) return launch_pair<true>(a, S.n_steps, n_rays, dev, st);
         mlp_bf16_kernel<false, 0, true><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, nullptr);
         return check_launch("inerf_mlp_fwd_train[bf16]");
     }
@@ -1013,31 +1045,7 @@ int mlp_bf16_launch(const MlpArgs& a, bool embedded, cudaStream_t st) {
         mlp_bf16_kernel<true><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, a.trace);
         return check_launch("inerf_mlp_fwd[bf16]");
     }
-    // inference: the CTA-pair build (clusters of two; INERF_MLP_PAIR=0, read once, keeps the single-CTA kernel for A/B runs)
-    static const bool use_pair = [] { const char* e = getenv("INERF_MLP_PAIR"); return !e || atoi(e) != 0; }();
-    if (use_pair && num_sms() >= 2) {
-        static thread_local int pair_dev = -1;
-        if (pair_dev != dev) {
-            cudaError_t e = cudaFuncSetAttribute(mlp_bf16_kernel<false, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
-            if (e != cudaSuccess) { set_error("mlp_bf16: setup: %s", cudaGetErrorString(e)); return (int)e; }
-            pair_dev = dev;
-        }
-        const long long n_pair_iter = (a.P + 511) / 512;
-        const long long max_pairs = num_sms() / 2;
-        const long long pairs = n_pair_iter < max_pairs ? n_pair_iter : max_pairs;
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)(2 * pairs));
-        cfg.blockDim = dim3(NTHREADS_BF16);
-        cfg.dynamicSmemBytes = SMEM_ALLOC;
-        cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_bf16_kernel<false, 0, false, true>, a, S.n_steps, n_rays, (float*)nullptr);
-        if (e != cudaSuccess) { set_error("inerf_mlp_fwd[bf16 pair]: %s", cudaGetErrorString(e)); return (int)e; }
-        return check_launch("inerf_mlp_fwd[bf16 pair]");
-    }
+    if (use_pair) return launch_pair<false>(a, S.n_steps, n_rays, dev, st);
     mlp_bf16_kernel<false><<<grid, NTHREADS_BF16, SMEM_ALLOC, st>>>(a, S.n_steps, n_rays, nullptr);
     return check_launch("inerf_mlp_fwd[bf16]");
 }

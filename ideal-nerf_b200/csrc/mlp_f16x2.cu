@@ -43,6 +43,9 @@ namespace {
 
 constexpr int NSTAGE = 3;
 constexpr int STAGE_BYTES = 16384;
+// CTA-pair build (PAIR = true, see mlp_bf16.cu): each CTA of a cluster of two holds HALF of the rows of every weight stage; the same 48 KB
+// ring is six stages deep
+template <bool PAIR> struct RingOf { static constexpr int N = PAIR ? 6 : 3, BYTES = PAIR ? 8192 : 16384; };
 constexpr int MAX_FSTAGES = 160;     // 76 K-block steps x (hi, lo)
 constexpr int RMAX = 4;              // rays a 128-row slot can touch (s >= 43)
 constexpr int NTHREADS = 512;
@@ -81,18 +84,21 @@ constexpr int OFF_RW = OFF_AW + 1024;                    // rgb_linear.weight 3x
 constexpr int OFF_DIRB = OFF_RW + 1536;                  // [RMAX][128] floats
 constexpr int OFF_PART = OFF_DIRB + RMAX * 128 * 4;      // [128 rows] float4: head partial sums of epilogue group 1
 constexpr int OFF_BAR = OFF_PART + 128 * 16;             // mbarriers
-constexpr int SMEM_BYTES = OFF_BAR + 256;
+constexpr int SMEM_BYTES = OFF_BAR + 320;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 constexpr int BF16_TILE_BYTES = 16 * 4096 + 6 * 2048;    // the bf16 kernel's bias tiles come first in `cond`; ours follow
 
 struct Bars {
-    uint64_t wfull[NSTAGE], wempty[NSTAGE];
-    uint64_t cbar[3];        // C0, C1, C2   (tcgen05.commit, once per layer)
-    uint64_t ebar[2];        // E0, E1       (8 epilogue warps, once per layer)
+    uint64_t wfull[6], wempty[6];
+    uint64_t pfull[6];       // pair build, leader only: the PEER's half of the stage has landed (relayed by the peer's warp 1)
+    uint64_t cbar[3];        // C0, C1, C2   (tcgen05.commit, once per layer; pair build: multicast to both CTAs)
+    uint64_t ebar[2];        // E0, E1       (8 epilogue warps, once per layer; pair build: the leader's, 8 + 8 warps)
     uint64_t pe_ready, pe_free, dirb_ready, dirb_free;
     uint64_t bfull[2], bempty[2];
+    uint64_t pbfull[2];      // pair build, leader only: the peer's half of the bias tile has landed
     uint32_t tmem_base;
 };
+static_assert(sizeof(Bars) <= 320, "barrier block");
 
 // The MMA issuer's waits sit on the critical path of the tensor pipe (the bf16 kernel lost 3 % when its issuer got the bounded form):
 // the issuer polls with the plain try_wait loop; every wait it depends on is made by a warp that IS bounded, so a protocol error still
@@ -130,6 +136,31 @@ __device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
         "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ void umma_lohi_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+template <bool PAIR>
+__device__ __forceinline__ void umma_any(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (PAIR) umma_lohi_pair(tmem_d, a_lo, b_lo, hi, idesc, accumulate);
+    else umma_lohi(tmem_d, a_lo, b_lo, hi, idesc, accumulate);
+}
+template <bool PAIR>
+__device__ __forceinline__ void commit_any(uint64_t* bar) {
+    if constexpr (PAIR) umma_commit_pair(bar);
+    else umma_commit(bar);
+}
+// issuer-side wait on an event whose arrivals may come from the peer CTA
+template <bool PAIR>
+__device__ __forceinline__ void wait_ev(uint64_t* bar, uint32_t parity) {
+    if constexpr (PAIR) mbar_wait_cluster(bar, parity);
+    else mbar_wait(bar, parity);
 }
 
 // 32 lanes x 16 consecutive 32-bit columns
@@ -184,13 +215,14 @@ struct IssueCtx {
 };
 
 // All MMAs of layer L, straight-line: every descriptor offset, wait and commit is a compile-time constant of (L, half, K-block).
-template <int L>
+template <int L, bool PAIR>
 __device__ __forceinline__ void issue_layer(IssueCtx& c) {
+    constexpr int NSTAGE = RingOf<PAIR>::N, STAGE_BYTES = RingOf<PAIR>::BYTES;
     constexpr int N = lay_N(L), NH = N / 2, NKB = lay_act_kb(L), CNT = NKB + (lay_pe(L) ? 1 : 0);
     constexpr int KB_PER_HALF_PREV = lay_prev_N(L) / 128;
     constexpr int N_OUT_H0 = NH / 64;
     constexpr int N_FIRST = NKB < N_OUT_H0 ? NKB : N_OUT_H0;
-    constexpr uint32_t IDESC = idesc_f16(128, NH);
+    constexpr uint32_t IDESC = idesc_f16(PAIR ? 256 : 128, NH);
     Bars* bars = c.bars;
     const uint32_t par_prev = (c.layer_ctr - 1) & 1;
 #pragma unroll
@@ -200,48 +232,53 @@ __device__ __forceinline__ void issue_layer(IssueCtx& c) {
             const bool is_pe = (i == NKB);
             if (h == 0 && c.layer_ctr > 0) {
                 if (L == 0) {
-                    if (i == 0) { wait_i(&bars->ebar[0], par_prev); wait_i(&bars->ebar[1], par_prev); }
+                    if (i == 0) { wait_ev<PAIR>(&bars->ebar[0], par_prev); wait_ev<PAIR>(&bars->ebar[1], par_prev); }
                 } else if (!is_pe) {
-                    if (i == 0) wait_i(&bars->ebar[0], par_prev);
-                    if (i == KB_PER_HALF_PREV) wait_i(&bars->ebar[1], par_prev);
+                    if (i == 0) wait_ev<PAIR>(&bars->ebar[0], par_prev);
+                    if (i == KB_PER_HALF_PREV) wait_ev<PAIR>(&bars->ebar[1], par_prev);
                 }
             }
-            if (L == 0 && h == 0 && i == 0) wait_i(&bars->pe_ready, c.iter_ctr & 1);
+            if (L == 0 && h == 0 && i == 0) wait_ev<PAIR>(&bars->pe_ready, c.iter_ctr & 1);
             const uint32_t d = c.tmem_base + h * NH, dc = d + CORR_COL;      // main / correction accumulator
             const uint32_t a_hi = is_pe ? c.pe_lo : c.a_lo + i * (16384 >> 4);
             const uint32_t a_lo = is_pe ? c.pe_lo + (16384 >> 4) : c.a_lo + (65536 >> 4) + i * (16384 >> 4);
             // ---- stage 1: W_hi -- A_hi.W_hi -> main, A_lo.W_hi -> correction ------------------------------------------------
             wait_i(&bars->wfull[c.stage], c.wpar);
-            if (i == 0) wait_i(&bars->bfull[c.bslot], c.bpar);
+            if constexpr (PAIR) mbar_wait_cluster(&bars->pfull[c.stage], c.wpar);
+            if (i == 0) {
+                wait_i(&bars->bfull[c.bslot], c.bpar);
+                if constexpr (PAIR) mbar_wait_cluster(&bars->pbfull[c.bslot], c.bpar);
+            }
             tc_fence_after();
             if (elect_one()) {
                 if (i == 0) {      // bias: D = ones[128x16] . tile[NHx16]^T, tile columns (hi, mid, lo, 0, ...); overwrites the accumulator
-                    umma_lohi(d, c.ones_lo, c.bt_lo + c.bslot * (4096 >> 4), HI_NOSWZ, IDESC, 0u);
-                    umma_commit(&bars->bempty[c.bslot]);
+                    umma_any<PAIR>(d, c.ones_lo, c.bt_lo + c.bslot * (4096 >> 4), HI_NOSWZ, IDESC, 0u);
+                    commit_any<PAIR>(&bars->bempty[c.bslot]);
                 }
                 const uint32_t b = c.w_lo + c.stage * (STAGE_BYTES >> 4);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_lohi(d, a_hi + 2 * k, b + 2 * k, c.hi, IDESC, 1u);
+                for (int k = 0; k < 4; ++k) umma_any<PAIR>(d, a_hi + 2 * k, b + 2 * k, c.hi, IDESC, 1u);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_lohi(dc, a_lo + 2 * k, b + 2 * k, c.hi, IDESC, (i == 0 && k == 0) ? 0u : 1u);
-                umma_commit(&bars->wempty[c.stage]);
+                for (int k = 0; k < 4; ++k) umma_any<PAIR>(dc, a_lo + 2 * k, b + 2 * k, c.hi, IDESC, (i == 0 && k == 0) ? 0u : 1u);
+                commit_any<PAIR>(&bars->wempty[c.stage]);
             }
             __syncwarp();
             if (i == 0) { c.bslot ^= 1; if (c.bslot == 0) c.bpar ^= 1; }
             if (++c.stage == NSTAGE) { c.stage = 0; c.wpar ^= 1; }
             // ---- stage 2: W_lo -- A_hi.W_lo -> correction -------------------------------------------------------------------
             wait_i(&bars->wfull[c.stage], c.wpar);
+            if constexpr (PAIR) mbar_wait_cluster(&bars->pfull[c.stage], c.wpar);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t b = c.w_lo + c.stage * (STAGE_BYTES >> 4);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_lohi(dc, a_hi + 2 * k, b + 2 * k, c.hi, IDESC, 1u);
-                umma_commit(&bars->wempty[c.stage]);
+                for (int k = 0; k < 4; ++k) umma_any<PAIR>(dc, a_hi + 2 * k, b + 2 * k, c.hi, IDESC, 1u);
+                commit_any<PAIR>(&bars->wempty[c.stage]);
                 const bool last = (i == CNT - 1);
-                if (h == 0 && last) umma_commit(&bars->cbar[0]);
-                if (h == 1 && (N_FIRST > 0 ? i == N_FIRST - 1 : last)) umma_commit(&bars->cbar[1]);
-                if (h == 1 && last) umma_commit(&bars->cbar[2]);
-                if (h == 1 && last && L == 5) umma_commit(&bars->pe_free);
+                if (h == 0 && last) commit_any<PAIR>(&bars->cbar[0]);
+                if (h == 1 && (N_FIRST > 0 ? i == N_FIRST - 1 : last)) commit_any<PAIR>(&bars->cbar[1]);
+                if (h == 1 && last) commit_any<PAIR>(&bars->cbar[2]);
+                if (h == 1 && last && L == 5) commit_any<PAIR>(&bars->pe_free);
             }
             __syncwarp();
             if (++c.stage == NSTAGE) { c.stage = 0; c.wpar ^= 1; }
@@ -285,7 +322,11 @@ __device__ __forceinline__ void epi16(const uint32_t (&r)[16], const uint32_t (&
 
 // abl (profiling only, INERF_F16X2_ABL; results are garbage): bit 0 = the weight ring is filled once and never reloaded, bit 1 = the
 // epilogue keeps its barrier protocol but skips the TMEM loads / conversion / stores, bit 2 = the positional-encoding warps skip sincosf
+// PAIR = true: clusters of two CTAs, one tcgen05.mma.cta_group::2 over the 2 x 128 rows of the pair, the weight stages split across the
+// pair (the bf16 kernel's pair build, mlp_bf16.cu; a pair iteration is two 128-point slots, CTA r takes slot 2 it + r).
+template <bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1) mlp_f16x2_kernel(MlpArgs a, int n_stages, int n_rays, int abl) {
+    constexpr int NSTAGE = RingOf<PAIR>::N, STAGE_BYTES = RingOf<PAIR>::BYTES;
     extern __shared__ __align__(1024) uint8_t sm[];
     if ((smem_u32(sm) & 1023u) != 0) __trap();
     Bars* bars = reinterpret_cast<Bars*>(sm + OFF_BAR);
@@ -296,7 +337,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_f16x2_kernel(MlpArgs a, int n
     float4* s_part = reinterpret_cast<float4*>(sm + OFF_PART);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long n_iter = (a.P + 127) / 128;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const long long n_iter = PAIR ? (a.P + 255) / 256 : (a.P + 127) / 128;
+    const long long it_first = PAIR ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+    const long long it_step = PAIR ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
+#define SLOT_OF(it_) (PAIR ? 2 * (it_) + (long long)rank : (it_))
 
     // ---- one-time setup -------------------------------------------------------------------
     if (tid < 4) s_sb[tid] = a.cond[8 * 256 + 3 * 128 + tid];
@@ -306,22 +351,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_f16x2_kernel(MlpArgs a, int n
     for (int i = tid; i < 256; i += NTHREADS) s_aw[i] = a.w[P_ALPHA_W][i];
     for (int i = tid; i < 384; i += NTHREADS) s_rw[i] = a.w[P_RGB_W][i];
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars->wfull[s], 1); mbar_init(&bars->wempty[s], 1); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars->wfull[s], 1); mbar_init(&bars->wempty[s], 1); mbar_init(&bars->pfull[s], 1); }
         for (int j = 0; j < 3; ++j) mbar_init(&bars->cbar[j], 1);
-        for (int j = 0; j < 2; ++j) mbar_init(&bars->ebar[j], N_EPI / 32);
-        mbar_init(&bars->pe_ready, N_PE);
+        for (int j = 0; j < 2; ++j) mbar_init(&bars->ebar[j], PAIR ? 2 * (N_EPI / 32) : N_EPI / 32);
+        mbar_init(&bars->pe_ready, PAIR ? 2 * (N_PE / 32) : N_PE);
         mbar_init(&bars->pe_free, 1);
         mbar_init(&bars->dirb_ready, N_PE);
         mbar_init(&bars->dirb_free, N_EPI / 32);
-        for (int j = 0; j < 2; ++j) { mbar_init(&bars->bfull[j], 1); mbar_init(&bars->bempty[j], 1); }
+        for (int j = 0; j < 2; ++j) { mbar_init(&bars->bfull[j], 1); mbar_init(&bars->bempty[j], 1); mbar_init(&bars->pbfull[j], 1); }
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(&bars->tmem_base, 512);
-        tmem_relinquish();
+        if constexpr (PAIR) {
+            tmem_alloc_pair(&bars->tmem_base, 512);
+        } else {
+            tmem_alloc(&bars->tmem_base, 512);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
@@ -331,26 +381,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_f16x2_kernel(MlpArgs a, int n
             const uint8_t* blob = reinterpret_cast<const uint8_t*>(a.packed);
             const uint8_t* tiles = reinterpret_cast<const uint8_t*>(a.cond + 2436) + BF16_TILE_BYTES;
             uint32_t g = 0, bh = 0;
-            for (long long it = blockIdx.x; it < n_iter; it += gridDim.x) {
+            constexpr uint32_t SPLIT = PAIR ? 2u : 1u;      // pair build: this CTA's half of the rows of every stage / bias tile
+            for (long long it = it_first; it < n_iter; it += it_step) {
                 for (int s = 0; s < n_stages; ++s, ++g) {
                     const uint32_t stage = g % NSTAGE, round = g / NSTAGE;
                     const FStage fs = c_fstages[s];
                     if (fs.bias) {
                         const uint32_t slot = bh & 1, l = fs.layer, h = fs.half;
-                        const uint32_t bytes = (uint32_t)fs.n8 * 8u * 32u;
-                        const uint32_t off = l < 8 ? (2 * l + h) * 4096u : 65536u + (2 * (l - 8) + h) * 2048u;
+                        const uint32_t bytes = (uint32_t)fs.n8 * 8u * 32u / SPLIT;
+                        const uint32_t off = (l < 8 ? (2 * l + h) * 4096u : 65536u + (2 * (l - 8) + h) * 2048u) + rank * bytes;
                         wait_b(&bars->bempty[slot], ((bh >> 1) & 1) ^ 1);
                         mbar_arrive_expect_tx(&bars->bfull[slot], bytes);
                         bulk_g2s(sm + OFF_BT + slot * 4096, tiles + off, bytes, &bars->bfull[slot]);
                         ++bh;
                     }
                     wait_b(&bars->wempty[stage], (round & 1) ^ 1);
-                    const uint32_t bytes = (uint32_t)fs.n8 * 8u * 128u;
+                    const uint32_t bytes = (uint32_t)fs.n8 * 8u * 128u / SPLIT;
                     if ((abl & 1) && g >= NSTAGE) { mbar_arrive(&bars->wfull[stage]); continue; }
                     mbar_arrive_expect_tx(&bars->wfull[stage], bytes);
-                    bulk_g2s(sm + OFF_W + stage * STAGE_BYTES, blob + fs.offset, bytes, &bars->wfull[stage]);
+                    bulk_g2s(sm + OFF_W + stage * STAGE_BYTES, blob + fs.offset + rank * bytes, bytes, &bars->wfull[stage]);
                 }
             }
+        }
+    } else if (warp == 1 && PAIR && rank != 0) {
+        // ================= relay (peer CTA of a pair): tell the leader when MY half of a bias tile / weight stage has landed =========
+        if (lane == 0) {
+            uint32_t g = 0, bh = 0;
+            for (long long it = it_first; it < n_iter; it += it_step)
+                for (int s = 0; s < n_stages; ++s, ++g) {
+                    if (c_fstages[s].bias) {
+                        mbar_wait(&bars->bfull[bh & 1], (bh >> 1) & 1);
+                        mbar_arrive_remote(&bars->pbfull[bh & 1], 0);
+                        ++bh;
+                    }
+                    mbar_wait(&bars->wfull[g % NSTAGE], (g / NSTAGE) & 1);
+                    mbar_arrive_remote(&bars->pfull[g % NSTAGE], 0);
+                }
         }
     } else if (warp == 1) {
         // ================= MMA issuer (whole warp converged; one elected lane issues) ==========
@@ -365,17 +431,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_f16x2_kernel(MlpArgs a, int n
         c.bt_lo = desc_lo_noswz(smem_u32(sm + OFF_BT));
         c.bslot = 0; c.bpar = 0;
         c.stage = 0; c.wpar = 0; c.layer_ctr = 0; c.iter_ctr = 0;
-        for (long long it = blockIdx.x; it < n_iter; it += gridDim.x, ++c.iter_ctr) {
-            issue_layer<0>(c);
+        for (long long it = it_first; it < n_iter; it += it_step, ++c.iter_ctr) {
+            issue_layer<0, PAIR>(c);
 #pragma unroll 1
             for (int seg = 0; seg < 2; ++seg) {
 #pragma unroll 1
-                for (int r = 0; r < (seg ? 2 : 4); ++r) issue_layer<1>(c);
-                if (seg == 0) issue_layer<5>(c);
+                for (int r = 0; r < (seg ? 2 : 4); ++r) issue_layer<1, PAIR>(c);
+                if (seg == 0) issue_layer<5, PAIR>(c);
             }
-            issue_layer<8>(c);
+            issue_layer<8, PAIR>(c);
 #pragma unroll 1
-            for (int r = 0; r < 2; ++r) issue_layer<9>(c);
+            for (int r = 0; r < 2; ++r) issue_layer<9, PAIR>(c);
         }
     } else if (warp >= 4 && warp < 12) {
         // ================= epilogue: one row per thread, the two warp groups split the column chunks ======================
@@ -386,12 +452,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_f16x2_kernel(MlpArgs a, int n
         const uint32_t row_off = (row >> 3) * 1024 + (row & 7) * 128;
         const uint32_t rsw = row & 7;
         uint32_t layer_ctr = 0, iter_ctr = 0;
-        for (long long it = blockIdx.x; it < n_iter; it += gridDim.x, ++iter_ctr) {
-            const long long p0 = it * 128;
+        for (long long it = it_first; it < n_iter; it += it_step, ++iter_ctr) {
+            const long long p0 = SLOT_OF(it) * 128;
             long long p = p0 + row;
             const bool in_range = p < a.P;
             if (!in_range) p = a.P - 1;
-            const int ray_local = (int)(p / a.s - p0 / a.s);
+            const int ray_local = (int)(p / a.s - min(p0, a.P - 1) / a.s);
             float alpha = 0.f, rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
             for (int l = 0; l < 11; ++l, ++layer_ctr) {
                 const int NH = (l < 8 ? 256 : 128) >> 1;
@@ -450,7 +516,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_f16x2_kernel(MlpArgs a, int n
                         fence_proxy_async_smem();
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars->ebar[h]);
+                    if (lane == 0) { if constexpr (PAIR) mbar_arrive_remote(&bars->ebar[h], 0); else mbar_arrive(&bars->ebar[h]); }
                 }
                 if (l == 8) {
                     __syncwarp();
@@ -483,11 +549,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_f16x2_kernel(MlpArgs a, int n
             for (int j = 0; j < 27; ++j) wdir[j] = wrow[j];
         }
         uint32_t iter_ctr = 0;
-        for (long long it = blockIdx.x; it < n_iter; it += gridDim.x, ++iter_ctr) {
+        for (long long it = it_first; it < n_iter; it += it_step, ++iter_ctr) {
             // ---- gamma_10(o + d z) of row t, every octave with its own sincosf (2^k scaling is exact) -----------------------
             uint32_t pkh[32], pkl[32];
             {
-                long long p = it * 128 + t;
+                long long p = SLOT_OF(it) * 128 + t;
                 if (p > a.P - 1) p = a.P - 1;
                 const long long ray = p / a.s;
                 const float* r = a.rays + ray * a.ray_stride;
@@ -520,12 +586,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_f16x2_kernel(MlpArgs a, int n
                 }
             }
             fence_proxy_async_smem();
-            mbar_arrive(&bars->pe_ready);
+            if constexpr (PAIR) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(&bars->pe_ready, 0);
+            } else {
+                mbar_arrive(&bars->pe_ready);
+            }
             // ---- per-ray view bias: lane q < RMAX encodes ray q of the slot, the warp shares it by shuffle ----
             {
                 float enc[27];
                 if (lane < RMAX) {
-                    long long pfirst = it * 128;
+                    long long pfirst = SLOT_OF(it) * 128;
                     if (pfirst > a.P - 1) pfirst = a.P - 1;
                     long long ray = pfirst / a.s + lane;
                     if (ray > n_rays - 1) ray = n_rays - 1;
@@ -559,7 +630,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_f16x2_kernel(MlpArgs a, int n
     // ---- teardown ---------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if constexpr (PAIR) {
+        cluster_sync_all();      // nobody leaves while the peer may still arrive on / multicast to this CTA
+        if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
+    } else {
+        if (warp == 2) tmem_dealloc(tmem_base, 512);
+    }
+#undef SLOT_OF
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -658,7 +735,8 @@ int mlp_f16x2_launch(const MlpArgs& a, cudaStream_t st) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (configured_dev != dev) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_f16x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(mlp_f16x2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_f16x2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_fstages, S.st, sizeof(FStage) * MAX_FSTAGES);
         if (e != cudaSuccess) { set_error("mlp_f16x2: setup: %s", cudaGetErrorString(e)); return (int)e; }
         configured_dev = dev;
@@ -672,7 +750,26 @@ int mlp_f16x2_launch(const MlpArgs& a, cudaStream_t st) {
     if (const char* e = getenv("INERF_F16X2_ULPS")) sscanf(e, "%f,%f,%f,%f", &b.tc_ulps[0], &b.tc_ulps[1], &b.tc_ulps[2], &b.tc_ulps[3]);
     int abl = 0;
     if (const char* e = getenv("INERF_F16X2_ABL")) abl = atoi(e);
-    mlp_f16x2_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(b, S.n_stages, (int)(a.P / a.s), abl);
+    // the CTA-pair build by default; INERF_MLP_PAIR=0 (read once) keeps the single-CTA kernel for A/B runs
+    static const bool pair_env = [] { const char* e = getenv("INERF_MLP_PAIR"); return !e || atoi(e) != 0; }();
+    if (pair_env && num_sms() >= 2) {
+        const long long n_pair_iter = (a.P + 255) / 256;
+        const long long max_pairs = num_sms() / 2;
+        const long long pairs = n_pair_iter < max_pairs ? n_pair_iter : max_pairs;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(2 * pairs));
+        cfg.blockDim = dim3(NTHREADS);
+        cfg.dynamicSmemBytes = SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_f16x2_kernel<true>, b, S.n_stages, (int)(a.P / a.s), abl);
+        if (e != cudaSuccess) { set_error("inerf_mlp_fwd[fp16x2 pair]: %s", cudaGetErrorString(e)); return (int)e; }
+        return check_launch("inerf_mlp_fwd[fp16x2 pair]");
+    }
+    mlp_f16x2_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(b, S.n_stages, (int)(a.P / a.s), abl);
     return check_launch("inerf_mlp_fwd[fp16x2]");
 }
 

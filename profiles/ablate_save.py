@@ -55,6 +55,13 @@ with torch.no_grad():
 print(f"render forward (no saving)                         {ms:7.3f} ms")
 names = {0: "training forward, everything saved", 1: "no mask stores", 2: "no bulk copies of the activation images", 4: "no PE / view images",
          3: "no masks, no bulk copies", 7: "nothing saved (SAVE code paths only)"}
+if "--waits" in sys.argv:      # round 3: is it the wait for the bulk copies' shared-memory reads (latency) or their bandwidth?
+    names.update({8: "everything saved, NO wait for the copies' smem reads (rows overwritten early: garbage images)", 10: "no bulk copies, no waits"})
+    for abl in (0, 8, 2, 1, 9):
+        os.environ["INERF_SAVE_ABL"] = str(abl)
+        ms = timed(lambda: ops.mlp_fwd_train_bf16(f._dims, params, packed, cond, rays, z))
+        print(f"SAVE_ABL={abl} {names.get(abl, 'masks off + no waits'):64s} {ms:7.3f} ms")
+    sys.exit(0)
 for kabl, ktag in ((0, ""), (2, " + weight streaming off"), (4, " + sincosf off")):
     os.environ["INERF_ABL"] = str(kabl)
     for abl in (0, 1, 2, 4, 3, 7) if kabl == 0 else (0, 2, 7):
