@@ -14,6 +14,7 @@
 // memory for the next GEMM and to HBM as a 16 KB image per 64 features for the dW kernel (mlp_bf16_dw.cu).  Four "init" warps turn
 // d_raw into d_v2 = (d_rgb . rgb_linear.weight) * mask, the d_sigma operand tile and the d_raw image of the next iteration.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "mlp_common.cuh"
 #include "sm100_ptx.cuh"
@@ -25,6 +26,9 @@ namespace {
 
 constexpr int NSTAGE = 4;
 constexpr int STAGE_BYTES = 16384;
+// CTA-pair build (PAIR = true, see mlp_bf16.cu): each CTA of a cluster of two holds HALF of the rows of every weight stage; the same 64 KB
+// ring is eight stages deep
+template <bool PAIR> struct RingOf { static constexpr int N = PAIR ? 8 : 4, BYTES = PAIR ? 8192 : 16384; };
 constexpr int NTH = 512;
 constexpr int N_EPI = 256, N_INIT = 128;
 constexpr int NLAY = 10;
@@ -45,13 +49,15 @@ constexpr int SMEM_BWD = OFF_BAR + 256;
 static_assert(SMEM_BWD <= 232448, "shared memory budget");
 
 struct Bars {
-    uint64_t wfull[NSTAGE], wempty[NSTAGE];
-    uint64_t cbar[3];        // C0, C1, C2
-    uint64_t ebar[2];        // E0, E1 (8 epilogue warps)
-    uint64_t init_ready;     // 4 init warps, once per iteration
+    uint64_t wfull[8], wempty[8];
+    uint64_t pfull[8];       // pair build, leader only: the PEER's half of the stage has landed (relayed by the peer's warp 1)
+    uint64_t cbar[3];        // C0, C1, C2 (pair build: multicast to both CTAs)
+    uint64_t ebar[2];        // E0, E1 (8 epilogue warps; pair build: the leader's, 8 + 8 warps)
+    uint64_t init_ready;     // 4 init warps, once per iteration (pair build: the leader's, 4 + 4 warps)
     uint64_t init_free;      // commit after the last MMA of the iteration
     uint32_t tmem_base;
 };
+static_assert(sizeof(Bars) <= 256, "barrier block");
 
 struct BwdChainArgs {
     const void* packed_t;          // transposed weight stages + the two alpha tiles (inerf_mlp_pack, INERF_MLP_BF16_BWD)
@@ -88,6 +94,31 @@ __device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32
         "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc)
         : "memory");
 }
+__device__ __forceinline__ void umma_lohi_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+template <bool PAIR>
+__device__ __forceinline__ void umma_any(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+    if constexpr (PAIR) umma_lohi_pair(tmem_d, a_lo, b_lo, hi, idesc, acc);
+    else umma_lohi(tmem_d, a_lo, b_lo, hi, idesc, acc);
+}
+template <bool PAIR>
+__device__ __forceinline__ void commit_any(uint64_t* bar) {
+    if constexpr (PAIR) umma_commit_pair(bar);
+    else umma_commit(bar);
+}
+// issuer-side wait on an event whose arrivals may come from the peer CTA
+template <bool PAIR>
+__device__ __forceinline__ void wait_ev(uint64_t* bar, uint32_t parity) {
+    if constexpr (PAIR) mbar_wait_cluster(bar, parity);
+    else bwait(bar, parity);
+}
 
 constexpr uint32_t HI_NOSWZ = (256u >> 4) | (1u << 14);
 __device__ __forceinline__ uint32_t desc_lo_noswz(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | ((128u >> 4) << 16); }
@@ -98,13 +129,14 @@ struct IssueCtx {
     uint32_t stage, wpar, layer_ctr, iter_ctr;
 };
 
-template <int J>
+template <int J, bool PAIR>
 __device__ __forceinline__ void issue_layer(IssueCtx& c) {
+    constexpr int NSTAGE = RingOf<PAIR>::N, STAGE_BYTES = RingOf<PAIR>::BYTES;
     constexpr int N = bl_N(J), NH = N / 2, NKB = bl_kb(J);
     constexpr int KB_PER_HALF_PREV = bl_prev_N(J) / 128;
     constexpr int N_OUT_H0 = NH / 64;
     constexpr int N_FIRST = NKB < N_OUT_H0 ? NKB : N_OUT_H0;
-    constexpr uint32_t IDESC = umma_idesc_bf16(128, NH);
+    constexpr uint32_t IDESC = umma_idesc_bf16(PAIR ? 256 : 128, NH);
     Bars* bars = c.bars;
     const uint32_t par_prev = (c.layer_ctr - 1) & 1;
 #pragma unroll
@@ -114,21 +146,22 @@ __device__ __forceinline__ void issue_layer(IssueCtx& c) {
             if (h == 0 && c.layer_ctr > 0) {
                 if (J == 0 || bl_N(J) > bl_prev_N(J)) {        // new iteration, or a layer WIDER than the previous one: its first half
                     // overwrites accumulator columns that both halves of the previous epilogue read
-                    if (i == 0) { bwait(&bars->ebar[0], par_prev); bwait(&bars->ebar[1], par_prev); }
+                    if (i == 0) { wait_ev<PAIR>(&bars->ebar[0], par_prev); wait_ev<PAIR>(&bars->ebar[1], par_prev); }
                 } else {
-                    if (i == 0) bwait(&bars->ebar[0], par_prev);
-                    if (i == KB_PER_HALF_PREV) bwait(&bars->ebar[1], par_prev);
+                    if (i == 0) wait_ev<PAIR>(&bars->ebar[0], par_prev);
+                    if (i == KB_PER_HALF_PREV) wait_ev<PAIR>(&bars->ebar[1], par_prev);
                 }
             }
-            if (J == 0 && h == 0 && i == 0) bwait(&bars->init_ready, c.iter_ctr & 1);
+            if (J == 0 && h == 0 && i == 0) wait_ev<PAIR>(&bars->init_ready, c.iter_ctr & 1);
             bwait(&bars->wfull[c.stage], c.wpar);
+            if constexpr (PAIR) mbar_wait_cluster(&bars->pfull[c.stage], c.wpar);
             tc_fence_after();
             if (elect_one()) {
                 if (J == 2 && i == 0) {
                     // d h7 += d_sigma (x) alpha_linear.weight: A row = (s_hi, s_hi, s_lo, s_lo, 0...), B row = (w_hi, w_lo, w_hi, w_lo, 0...)
 #pragma unroll
                     for (int slot = 0; slot < 2; ++slot)
-                        umma_lohi(c.tmem_base + slot * 256 + h * NH, c.ds_lo + slot * (4096 >> 4), c.awt_lo + h * (4096 >> 4), HI_NOSWZ, IDESC, 0u);
+                        umma_any<PAIR>(c.tmem_base + slot * 256 + h * NH, c.ds_lo + slot * (4096 >> 4), c.awt_lo + h * (4096 >> 4), HI_NOSWZ, IDESC, 0u);
                 }
                 const uint32_t b_lo = c.w_lo + c.stage * (STAGE_BYTES >> 4);
 #pragma unroll
@@ -136,14 +169,14 @@ __device__ __forceinline__ void issue_layer(IssueCtx& c) {
                     const uint32_t a_lo = c.a_lo + slot * (65536 >> 4) + i * (16384 >> 4);
                     const uint32_t d = c.tmem_base + slot * 256 + h * NH;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_lohi(d, a_lo + 2 * k, b_lo + 2 * k, c.hi, IDESC, (J != 2 && i == 0 && k == 0) ? 0u : 1u);
+                    for (int k = 0; k < 4; ++k) umma_any<PAIR>(d, a_lo + 2 * k, b_lo + 2 * k, c.hi, IDESC, (J != 2 && i == 0 && k == 0) ? 0u : 1u);
                 }
-                umma_commit(&bars->wempty[c.stage]);
+                commit_any<PAIR>(&bars->wempty[c.stage]);
                 const bool last = (i == NKB - 1);
-                if (h == 0 && last) umma_commit(&bars->cbar[0]);
-                if (h == 1 && i == N_FIRST - 1) umma_commit(&bars->cbar[1]);
-                if (h == 1 && last) umma_commit(&bars->cbar[2]);
-                if (h == 1 && last && J == NLAY - 1) umma_commit(&bars->init_free);
+                if (h == 0 && last) commit_any<PAIR>(&bars->cbar[0]);
+                if (h == 1 && i == N_FIRST - 1) commit_any<PAIR>(&bars->cbar[1]);
+                if (h == 1 && last) commit_any<PAIR>(&bars->cbar[2]);
+                if (h == 1 && last && J == NLAY - 1) commit_any<PAIR>(&bars->init_free);
             }
             __syncwarp();
             if (++c.stage == NSTAGE) { c.stage = 0; c.wpar ^= 1; }
@@ -152,31 +185,48 @@ __device__ __forceinline__ void issue_layer(IssueCtx& c) {
     ++c.layer_ctr;
 }
 
+// PAIR = true: clusters of two CTAs, one tcgen05.mma.cta_group::2 over the 2 x 128 rows of the pair, the (transposed) weight stages split
+// across the pair; a pair iteration is two 256-point chunks, CTA r takes chunk 2 it + r (the forward kernel's pair build, mlp_bf16.cu).
+template <bool PAIR>
 __global__ void __launch_bounds__(NTH, 1) mlp_bf16_bwd_chain_kernel(BwdChainArgs a, int n_steps) {
+    constexpr int NSTAGE = RingOf<PAIR>::N, STAGE_BYTES = RingOf<PAIR>::BYTES;
     extern __shared__ __align__(1024) uint8_t sm[];
     if ((smem_u32(sm) & 1023u) != 0) __trap();
     Bars* bars = reinterpret_cast<Bars*>(sm + OFF_BAR);
     float* s_rw = reinterpret_cast<float*>(sm + OFF_RW);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long n_iter = (a.P + 255) / 256;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const long long n_iter = PAIR ? (a.P + 511) / 512 : (a.P + 255) / 256;
+    const long long it_first = PAIR ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+    const long long it_step = PAIR ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
+#define CHUNK_OF(it_) (PAIR ? 2 * (it_) + (long long)rank : (it_))
 
     for (int i = tid; i < 384; i += NTH) s_rw[i] = a.rgb_w[i];
-    {   // the alpha tiles are constants of the call: straight copy of their packed image
-        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(a.packed_t) + a.n_stage_bytes_total);
-        for (int i = tid; i < 2 * 4096 / 16; i += NTH) reinterpret_cast<uint4*>(sm + OFF_AWT)[i] = src[i];
+    {   // the alpha tiles are constants of the call: straight copy of their packed image (pair build: this CTA's half of the rows of each
+        // tile, placed at the tile's base, as the B operand of a cta_group::2 MMA is split)
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.packed_t) + a.n_stage_bytes_total;
+        constexpr int HALF = PAIR ? 2048 : 4096;
+        for (int i = tid; i < 2 * HALF / 16; i += NTH) {
+            const int tile = i / (HALF / 16), o = i - tile * (HALF / 16);
+            reinterpret_cast<uint4*>(sm + OFF_AWT + tile * 4096)[o] = reinterpret_cast<const uint4*>(src + tile * 4096 + rank * HALF)[o];
+        }
     }
     fence_proxy_async_smem();
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars->wfull[s], 1); mbar_init(&bars->wempty[s], 1); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars->wfull[s], 1); mbar_init(&bars->wempty[s], 1); mbar_init(&bars->pfull[s], 1); }
         for (int j = 0; j < 3; ++j) mbar_init(&bars->cbar[j], 1);
-        for (int j = 0; j < 2; ++j) mbar_init(&bars->ebar[j], N_EPI / 32);
-        mbar_init(&bars->init_ready, N_INIT / 32);
+        for (int j = 0; j < 2; ++j) mbar_init(&bars->ebar[j], PAIR ? 2 * (N_EPI / 32) : N_EPI / 32);
+        mbar_init(&bars->init_ready, PAIR ? 2 * (N_INIT / 32) : N_INIT / 32);
         mbar_init(&bars->init_free, 1);
         fence_mbar_init();
     }
-    if (warp == 2) { tmem_alloc(&bars->tmem_base, 512); tmem_relinquish(); }
+    if (warp == 2) {
+        if constexpr (PAIR) { tmem_alloc_pair(&bars->tmem_base, 512); }
+        else { tmem_alloc(&bars->tmem_base, 512); tmem_relinquish(); }
+    }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
@@ -185,13 +235,24 @@ __global__ void __launch_bounds__(NTH, 1) mlp_bf16_bwd_chain_kernel(BwdChainArgs
         if (lane == 0) {
             const uint8_t* blob = reinterpret_cast<const uint8_t*>(a.packed_t);
             uint32_t g = 0;
-            for (long long it = blockIdx.x; it < n_iter; it += gridDim.x)
+            constexpr uint32_t SPLIT = PAIR ? 2u : 1u;      // pair build: this CTA's half of the rows of every stage
+            for (long long it = it_first; it < n_iter; it += it_step)
                 for (int s = 0; s < n_steps; ++s, ++g) {
                     const uint32_t stage = g % NSTAGE, round = g / NSTAGE;
                     bwait(&bars->wempty[stage], (round & 1) ^ 1);
-                    const uint32_t bytes = (uint32_t)c_bsteps[s].n8 * 8u * 128u;
+                    const uint32_t bytes = (uint32_t)c_bsteps[s].n8 * 8u * 128u / SPLIT;
                     mbar_arrive_expect_tx(&bars->wfull[stage], bytes);
-                    bulk_g2s(sm + OFF_W + stage * STAGE_BYTES, blob + c_bsteps[s].offset, bytes, &bars->wfull[stage]);
+                    bulk_g2s(sm + OFF_W + stage * STAGE_BYTES, blob + c_bsteps[s].offset + rank * bytes, bytes, &bars->wfull[stage]);
+                }
+        }
+    } else if (warp == 1 && PAIR && rank != 0) {
+        // ================= relay (peer CTA of a pair): tell the leader when MY half of a weight stage has landed ======================
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (long long it = it_first; it < n_iter; it += it_step)
+                for (int s = 0; s < n_steps; ++s, ++g) {
+                    bwait(&bars->wfull[g % NSTAGE], (g / NSTAGE) & 1);
+                    mbar_arrive_remote(&bars->pfull[g % NSTAGE], 0);
                 }
         }
     } else if (warp == 1) {
@@ -205,13 +266,13 @@ __global__ void __launch_bounds__(NTH, 1) mlp_bf16_bwd_chain_kernel(BwdChainArgs
         c.awt_lo = desc_lo_noswz(smem_u32(sm + OFF_AWT));
         c.tmem_base = tmem_base;
         c.stage = 0; c.wpar = 0; c.layer_ctr = 0; c.iter_ctr = 0;
-        for (long long it = blockIdx.x; it < n_iter; it += gridDim.x, ++c.iter_ctr) {
+        for (long long it = it_first; it < n_iter; it += it_step, ++c.iter_ctr) {
             // layers 3..8 have the same geometry (256 x 256 after a 256-wide layer): one copy of the issue code, run six times,
             // keeps the kernel's SASS inside the instruction cache (see the forward kernel)
-            issue_layer<0>(c); issue_layer<1>(c); issue_layer<2>(c);
+            issue_layer<0, PAIR>(c); issue_layer<1, PAIR>(c); issue_layer<2, PAIR>(c);
 #pragma unroll 1
-            for (int r = 0; r < 6; ++r) issue_layer<3>(c);
-            issue_layer<9>(c);
+            for (int r = 0; r < 6; ++r) issue_layer<3, PAIR>(c);
+            issue_layer<9, PAIR>(c);
         }
     } else if (warp >= 4 && warp < 12) {
         // ================= epilogue: one row per thread ==================================================================
@@ -222,8 +283,10 @@ __global__ void __launch_bounds__(NTH, 1) mlp_bf16_bwd_chain_kernel(BwdChainArgs
         const uint32_t row_off = (row >> 3) * 1024 + (row & 7) * 128;
         const uint32_t rsw = row & 7;
         uint32_t layer_ctr = 0;
-        for (long long it = blockIdx.x; it < n_iter; it += gridDim.x) {
-            const size_t T = (size_t)it * 2 + slot;
+        for (long long it = it_first; it < n_iter; it += it_step) {
+            // pair build: the peer's last chunk may lie wholly past the end -- it reads tile 0's masks and writes nothing
+            const bool chunk_ok = !PAIR || CHUNK_OF(it) * 256 < a.P;
+            const size_t T = chunk_ok ? (size_t)CHUNK_OF(it) * 2 + slot : 0;
             for (int j = 0; j < NLAY; ++j, ++layer_ctr) {
                 const int N = j < 2 ? 128 : 256, NH = N >> 1, lo = 9 - j;      // lo: forward layer this delta belongs to
                 const uint32_t par = layer_ctr & 1;
@@ -256,7 +319,9 @@ __global__ void __launch_bounds__(NTH, 1) mlp_bf16_bwd_chain_kernel(BwdChainArgs
                         }
                     }
                     tc_fence_before();
-                    if (j == NLAY - 1) {
+                    if (j == NLAY - 1 && !chunk_ok) {
+                        // nothing to store
+                    } else if (j == NLAY - 1) {
                         // d_h0 feeds no further GEMM: straight to HBM (the init warps of the next iteration may already be refilling the
                         // shared-memory K-blocks, so they are not used as a staging buffer here)
 #pragma unroll
@@ -292,7 +357,8 @@ __global__ void __launch_bounds__(NTH, 1) mlp_bf16_bwd_chain_kernel(BwdChainArgs
                         if (lane == 0) {
                             const int kb0 = (h * NH) >> 6, nkb = NH >> 6;
                             const uint32_t wrow = (uint32_t)(warp & 3) * 4096u;
-                            for (int k = 0; k < nkb; ++k) bulk_s2g(gimg_base + (kb0 + k) * 16384 + wrow, act + (kb0 + k) * 16384 + wrow, 4096u);
+                            if (chunk_ok)
+                                for (int k = 0; k < nkb; ++k) bulk_s2g(gimg_base + (kb0 + k) * 16384 + wrow, act + (kb0 + k) * 16384 + wrow, 4096u);
                             bulk_commit();
                             // last copy of the iteration: the init warps refill K-blocks 0,1 once the final layer's MMAs are done, so the copy
                             // of those K-blocks (the previous half's) must have left shared memory before this half releases that layer
@@ -300,7 +366,7 @@ __global__ void __launch_bounds__(NTH, 1) mlp_bf16_bwd_chain_kernel(BwdChainArgs
                         }
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars->ebar[h]);
+                    if (lane == 0) { if constexpr (PAIR) mbar_arrive_remote(&bars->ebar[h], 0); else mbar_arrive(&bars->ebar[h]); }
                 }
             }
         }
@@ -313,12 +379,14 @@ __global__ void __launch_bounds__(NTH, 1) mlp_bf16_bwd_chain_kernel(BwdChainArgs
         const int t = tid - 12 * 32;             // row of both slots
         const uint32_t trow = (t >> 3) * 1024 + (t & 7) * 128, tsw = t & 7;
         uint32_t iter_ctr = 0;
-        for (long long it = blockIdx.x; it < n_iter; it += gridDim.x, ++iter_ctr) {
+        for (long long it = it_first; it < n_iter; it += it_step, ++iter_ctr) {
+            const long long chunk = CHUNK_OF(it);
+            const bool chunk_ok = !PAIR || chunk * 256 < a.P;      // a chunk wholly past the end: zero deltas, tile 0's masks, no stores
             float dsig[2];
 #pragma unroll 1
             for (int sl = 0; sl < 2; ++sl) {
-                const long long p = it * 256 + sl * 128 + t;
-                const size_t T = (size_t)it * 2 + sl;
+                const long long p = chunk * 256 + sl * 128 + t;
+                const size_t T = chunk_ok ? (size_t)chunk * 2 + sl : 0;
                 const float4 dr = (p < a.P) ? reinterpret_cast<const float4*>(a.d_raw)[p] : make_float4(0.f, 0.f, 0.f, 0.f);
                 dsig[sl] = dr.w;
                 const uint32_t* mp = a.mask + (T * TRAIN_MASK_WORDS + train_mask_of(10)) * 128 + t;
@@ -340,25 +408,26 @@ __global__ void __launch_bounds__(NTH, 1) mlp_bf16_bwd_chain_kernel(BwdChainArgs
                     const int ch0 = (w & 1) * 4;
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
-                        *reinterpret_cast<uint4*>(gk + (((ch0 + q) ^ tsw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                        if (chunk_ok) *reinterpret_cast<uint4*>(gk + (((ch0 + q) ^ tsw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 }
                 uint8_t* go = a.delta_img + (T * TRAIN_IMGS + TRAIN_IMG_DOUT) * 16384 + trow;      // columns 0..3 = d_rgb, d_sigma; zero elsewhere
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     uint4 v = make_uint4(0u, 0u, 0u, 0u);
                     if (q == 0) { v.x = pack_bf16x2(dr.x, dr.y); v.y = pack_bf16x2(dr.z, dr.w); }
-                    *reinterpret_cast<uint4*>(go + ((q ^ tsw) << 4)) = v;
+                    if (chunk_ok) *reinterpret_cast<uint4*>(go + ((q ^ tsw) << 4)) = v;
                 }
             }
             if (iter_ctr > 0) bwait(&bars->init_free, (iter_ctr - 1) & 1);
 #pragma unroll 1
             for (int sl = 0; sl < 2; ++sl) {
-                const size_t T = (size_t)it * 2 + sl;
+                const size_t T = chunk_ok ? (size_t)chunk * 2 + sl : 0;
                 const uint8_t* g2 = a.delta_img + (T * TRAIN_IMGS + train_img_of(10)) * 16384 + trow;
                 uint8_t* dst = sm + OFF_ACT + sl * 65536 + trow;
                 uint4 v[16];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = *reinterpret_cast<const uint4*>(g2 + (q >> 3) * 16384 + ((q & 7) << 4));
+                for (int q = 0; q < 16; ++q)
+                    v[q] = chunk_ok ? *reinterpret_cast<const uint4*>(g2 + (q >> 3) * 16384 + ((q & 7) << 4)) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                 for (int q = 0; q < 16; ++q) *reinterpret_cast<uint4*>(dst + (q >> 3) * 16384 + ((q & 7) << 4)) = v[q];
                 // d_sigma tile row: (hi, hi, lo, lo, 0, 0, 0, 0 | 0 x 8)
@@ -371,13 +440,19 @@ __global__ void __launch_bounds__(NTH, 1) mlp_bf16_bwd_chain_kernel(BwdChainArgs
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->init_ready);
+            if (lane == 0) { if constexpr (PAIR) mbar_arrive_remote(&bars->init_ready, 0); else mbar_arrive(&bars->init_ready); }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if constexpr (PAIR) {
+        cluster_sync_all();      // nobody leaves while the peer may still arrive on / multicast to this CTA
+        if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
+    } else {
+        if (warp == 2) tmem_dealloc(tmem_base, 512);
+    }
+#undef CHUNK_OF
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -479,7 +554,8 @@ int mlp_bf16_bwd_chain_launch(const InerfNetDims* dims, const float* const* para
     int dev = 0;
     cudaGetDevice(&dev);
     if (configured_dev != dev) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_bf16_bwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD);
+        cudaError_t e = cudaFuncSetAttribute(mlp_bf16_bwd_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bf16_bwd_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD);
         if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_bsteps, S.steps, sizeof(BStep) * MAX_BSTEPS);
         if (e != cudaSuccess) { set_error("mlp_bf16_bwd: setup: %s", cudaGetErrorString(e)); return (int)e; }
         configured_dev = dev;
@@ -489,7 +565,26 @@ int mlp_bf16_bwd_chain_launch(const InerfNetDims* dims, const float* const* para
     a.n_stage_bytes_total = S.stage_bytes;
     const long long n_iter = (P + 255) / 256;
     const int grid = (int)(n_iter < (long long)num_sms() ? n_iter : (long long)num_sms());
-    mlp_bf16_bwd_chain_kernel<<<grid, NTH, SMEM_BWD, st>>>(a, S.n_steps);
+    // the CTA-pair build by default; INERF_MLP_PAIR=0 (read once) keeps the single-CTA kernel for A/B runs
+    static const bool pair_env = [] { const char* e = getenv("INERF_MLP_PAIR"); return !e || atoi(e) != 0; }();
+    if (pair_env && num_sms() >= 2) {
+        const long long n_pair_iter = (P + 511) / 512;
+        const long long max_pairs = num_sms() / 2;
+        const long long pairs = n_pair_iter < max_pairs ? n_pair_iter : max_pairs;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(2 * pairs));
+        cfg.blockDim = dim3(NTH);
+        cfg.dynamicSmemBytes = SMEM_BWD;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_bf16_bwd_chain_kernel<true>, a, S.n_steps);
+        if (e != cudaSuccess) { set_error("inerf_mlp_bwd[bf16 chain pair]: %s", cudaGetErrorString(e)); return (int)e; }
+        return check_launch("inerf_mlp_bwd[bf16 chain pair]");
+    }
+    mlp_bf16_bwd_chain_kernel<false><<<grid, NTH, SMEM_BWD, st>>>(a, S.n_steps);
     return check_launch("inerf_mlp_bwd[bf16 chain]");
 }
 
