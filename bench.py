@@ -481,7 +481,10 @@ def run_ours(args):
     total_ms = timed(step_resident, args.steps)          # the headline: no per-kernel events inside this region
     launches = ops.LAUNCHES["count"]
     clocks = sampler.stop() if sampler else None
-    # second, identical pass with a CUDA-event pair around every launch (on the launching stream) for the roofline / breakdown
+    # second, identical pass with a CUDA-event pair around every launch (on the launching stream) for the roofline / breakdown; under
+    # kernel_timing the renderer takes the stage-by-stage entry points (one event pair per kernel), so that path gets its own warm-up
+    with ops.kernel_timing():
+        step_resident()
     with ops.kernel_timing() as kt:
         timed_ms_events = timed(step_resident, args.steps)
     ksum = kt.summary()
