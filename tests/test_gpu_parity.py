@@ -1232,6 +1232,56 @@ def test_fused_render_entry_bit_matches_stage_calls(M, golden, mode):
     assert {"rgb_map", "rgb0"} <= set(r["_nonfinite"]), r["_nonfinite"]
 
 
+_PAIR_VS_SINGLE = r"""
+import hashlib, sys, torch
+sys.path.insert(0, %r)
+import ideal_nerf_b200 as M
+from ideal_nerf_b200 import ops, synthetic as S
+dev = "cuda:0"
+cam, fr = S.camera(), S.frame_inputs(0)
+torch.manual_seed(3)
+net = M.FaceNeRF(dim_aud=64, dim_latent=32, dim_expr=76, mlp_mode="bf16").apply(M.init_weights).to(dev)
+aud, expr, lat = fr["aud"].to(dev), fr["expr"].to(dev), fr["latent"].to(dev)
+rays = ops.get_rays_range(450, 450, cam["focal"], cam["c2w"].to(dev), S.NEAR, S.FAR, 90000, 137)      # 137 x 64 -> 35 chunks, x 192 -> 103: odd
+h = hashlib.sha256()
+upd = lambda t: h.update(t.detach().contiguous().cpu().numpy().tobytes())
+params = [p.detach() for p in net.kernel_params()]
+with torch.no_grad():
+    for s in (64, 192):
+        z = torch.sort(S.NEAR + (S.FAR - S.NEAR) * torch.rand(137, s, device=dev, generator=torch.Generator(dev).manual_seed(s)), -1)[0].contiguous()
+        for mode in ("bf16", "fp16x2"):
+            net.mlp_mode = mode
+            upd(net.query(rays, z, aud, expr, lat))
+        net.mlp_mode = "bf16"
+        cond = ops.fold_cond(net._dims, params, aud, expr, lat)
+        raw, acts, mask, n_points = ops.mlp_fwd_train_bf16(net._dims, params, net.packed_weights(net.kernel_params()), cond, rays, z)
+        n_tiles = (n_points + 255) // 256 * 2
+        upd(raw); upd(acts); upd(mask)
+        d_raw = torch.randn(137, s, 4, device=dev, generator=torch.Generator(dev).manual_seed(7 + s))
+        ops.mlp_bwd_bf16(net._dims, params, net.packed_weights_bwd(net.kernel_params()), aud, expr, lat, acts, mask, d_raw, n_points, keep_deltas=True)
+        upd(ops.decode_images(ops.mlp_bwd_bf16.deltas, n_tiles)[:, :39])      # image 39 of the delta buffer is never written
+torch.cuda.synchronize()
+print("HASH", h.hexdigest())
+"""
+
+
+def test_pair_kernels_bit_match_single_cta_kernels(M):
+    """The CTA-pair builds (tcgen05 cta_group::2: inference bf16 / fp16x2, activation-saving forward, backward chain) against the
+    single-CTA kernels they replaced (INERF_MLP_PAIR=0, read once per process, hence two subprocesses): raw, the saved activation images
+    and ReLU masks, and the delta images agree BIT FOR BIT, on ray counts that give an odd number of 256-point chunks (the peer CTA's
+    last chunk lies past the end of the batch)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = []
+    for pair in ("1", "0"):
+        r = subprocess.run([sys.executable, "-c", _PAIR_VS_SINGLE % root], env={**os.environ, "INERF_MLP_PAIR": pair}, capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out.append([l for l in r.stdout.splitlines() if l.startswith("HASH")][-1])
+    assert out[0] == out[1], out
+
+
 def test_head_torso_frame_band_config4(M):
     """BASELINE.json config 4 at frame size: the head + torso composited 450 x 450 frame (test_torso.py:516-523; torso rays from the
     frame-0 camera, train_torso.py:132-134) -- three image rows of the frame against the oracle, fp32 mode, <= 1e-3."""
