@@ -1465,7 +1465,9 @@ def test_train_step_cuda_graph_matches_eager(M):
         # Adam's updates are sign-like (lr = 3e-4 per step whatever the gradient's size), so float-rounding differences of the atomic dW
         # reductions can flip individual updates: parameters agree to a fraction of the 8 x 3e-4 they can have moved
         close(q, p, 1.2e-3, f"parameter {k} after 8 steps")
-    close(steps[1].latent_codes, steps[0].latent_codes, 1e-4, "latent codes")
+    # every selected latent row gets ONE Adam step (|update| <= lr = 3e-4, sign-like); where its gradient component is ~0 the atomic
+    # rounding differences decide the update's size, so the bound is that one step, not float rounding (observed: up to 1.05e-4)
+    close(steps[1].latent_codes, steps[0].latent_codes, 3.1e-4, "latent codes")
     moved = (steps[1].latent_codes.detach() - 1.0).abs().amax(1) > 0
     assert moved.tolist() == [3 <= i < 11 for i in range(30)], "exactly the selected latent rows are trained"
     with pytest.raises(RuntimeError, match="fixed per TrainStep"):
