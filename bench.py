@@ -44,7 +44,7 @@ def peaks():
 def mlp_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the MLP kernel, mean per launch over the coarse and the fine pass, from the
     committed ncu --set full capture (profiles/); None when the summary is absent."""
-    p = os.path.join(ROOT, "profiles", "r02_mlp_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r03_mlp_traffic.json")
     if not os.path.exists(p):
         return None
     d = json.load(open(p))["dram_bytes_per_launch"]
