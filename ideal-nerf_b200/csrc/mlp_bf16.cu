@@ -343,6 +343,76 @@ __device__ __forceinline__ void issue_layer(IssueCtx& c) {
     ++c.layer_ctr;
 }
 
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// Epilogue of one layer WITHOUT head / view-bias work (L0-L6 and V1: eight of eleven), inference build, both halves as straight-line
+// code: tcgen05.ld, 16 conversions and (second half) 4 stores per 32-column chunk, store addresses = eight per-thread bases computed once
+// per kernel + immediates, no layer-kind or chunk-count branch between the chunks.  The general loop below spends a third of its stall
+// samples on instruction fetch and branch resolution around exactly this body (ncu source counters); instantiating that loop twice was
+// slower (register spills), a separate small function is not.  act_row: shared-memory address of this thread's row in K-block 0 of its
+// slot; soff[j] = byte offset of 16-byte chunk j of a 128-byte row after the swizzle.  ph: phase timers (INERF_PHASE_TIMERS builds).
+template <int NH, bool PAIR>
+__device__ __forceinline__ void epi_plain_layer(Bars* bars, uint32_t par, uint32_t t_lane, uint32_t act_row, const uint32_t (&soff)[8],
+                                                int lane, long long* ph) {
+    constexpr int NC = NH / 32;      // chunks per half: 4 (N = 256) or 2 (N = 128)
+    // ---- first half: convert everything, wait until the second half's MMAs have read the K-blocks it overwrites (C1), store ----------
+    const long long p0 = PH_CLK();
+    mbar_wait(&bars->cbar[0], par);
+    __syncwarp();
+    tc_fence_after();
+    const long long p1 = PH_CLK();
+    uint32_t packed[NC * 16];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_lane + c * 32, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) packed[c * 16 + j] = pack_bf16x2_relu(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+    }
+    tc_fence_before();
+    const long long p2 = PH_CLK();
+    mbar_wait(&bars->cbar[1], par);
+    ph[4] += PH_CLK() - p2;
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            sts128(act_row + ((c * 32) >> 6) * 16384 + soff[(((c * 32) & 63) >> 3) + q], packed[c * 16 + q * 4], packed[c * 16 + q * 4 + 1],
+                   packed[c * 16 + q * 4 + 2], packed[c * 16 + q * 4 + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) { if constexpr (PAIR) mbar_arrive_remote(&bars->ebar[0], 0); else mbar_arrive(&bars->ebar[0]); }
+    const long long p3 = PH_CLK();
+    ph[0] += p1 - p0; ph[1] += p3 - p1;
+    // ---- second half: nothing reads its K-blocks any more, every chunk is stored as soon as it is converted ----------------------------
+    mbar_wait(&bars->cbar[2], par);
+    __syncwarp();
+    tc_fence_after();
+    const long long p4 = PH_CLK();
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        uint32_t r[32], pk[16];
+        tmem_ld32(t_lane + NH + c * 32, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2_relu(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            sts128(act_row + ((NH + c * 32) >> 6) * 16384 + soff[(((NH + c * 32) & 63) >> 3) + q], pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) { if constexpr (PAIR) mbar_arrive_remote(&bars->ebar[1], 0); else mbar_arrive(&bars->ebar[1]); }
+    const long long p5 = PH_CLK();
+    ph[2] += p4 - p3; ph[3] += p5 - p4;
+}
+
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
@@ -519,6 +589,10 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
         uint8_t* act = sm + OFF_ACT + slot * 65536;
         const uint32_t row_off = (row >> 3) * 1024 + (row & 7) * 128;
         const uint32_t rsw = row & 7;
+        const uint32_t act_row_u32 = smem_u32(act) + row_off;
+        uint32_t soff[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) soff[j] = ((uint32_t)j ^ rsw) << 4;
         uint32_t layer_ctr = 0, iter_ctr = 0;
         long long te_wait = 0, te_ld = 0, te_c1 = 0, te_st = 0;       // trace build: epilogue phase cycles (warp 4)
         long long ph_wait[2] = {0, 0}, ph_dur[2] = {0, 0}, ph_c1 = 0;  // INERF_PHASE_TIMERS build: L1..L7, per half: wait for the commit / work until the arrival; wait for C1
@@ -535,6 +609,15 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                 const LayerInfo li = layer_info(l);
                 const int NH = li.N >> 1;
                 const uint32_t par = layer_ctr & 1;
+                if constexpr (!SAVE && !TRACE && ABL == 0) {      // inference: the layers without head / view-bias work take the straight-line epilogue
+                    long long phl[5] = {0, 0, 0, 0, 0};
+                    if (l <= 6) {
+                        epi_plain_layer<128, PAIR>(bars, par, t_lane, act_row_u32, soff, lane, phl);
+                        if (l >= 1) { ph_wait[0] += phl[0]; ph_dur[0] += phl[1]; ph_wait[1] += phl[2]; ph_dur[1] += phl[3]; ph_c1 += phl[4]; }
+                        continue;
+                    }
+                    if (l == 9) { epi_plain_layer<64, PAIR>(bars, par, t_lane, act_row_u32, soff, lane, phl); continue; }
+                }
                 if (l == 8) wait_or_report<TRACE>(&bars->dirb_ready, iter_ctr & 1, 301, l, (int)iter_ctr);
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
