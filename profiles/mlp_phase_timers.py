@@ -26,13 +26,22 @@ net = net.to(dev)
 rays = ops.get_rays_packed(450, 450, cam["focal"], cam["c2w"].to(dev), S.NEAR, S.FAR)
 z = torch.sort(S.NEAR + (S.FAR - S.NEAR) * torch.rand(rays.shape[0], 192, device=dev), -1)[0].contiguous()
 aud, expr, lat = fr["aud"].to(dev), fr["expr"].to(dev), fr["latent"].to(dev)
+TRAIN = "--train" in sys.argv          # the activation-saving forward on an N_rand = 3072 batch instead of the inference kernel on a frame
+if TRAIN:
+    rays, z = rays[:3072].contiguous(), z[:3072].contiguous()
+    params = [p.detach() for p in net.kernel_params()]
+    cond = ops.fold_cond(net._dims, params, aud, expr, lat)
+    packed = net.packed_weights(net.kernel_params())
+    run = lambda: ops.mlp_fwd_train_bf16(net._dims, params, packed, cond, rays, z)
+else:
+    run = lambda: net.query(rays, z, aud, expr, lat)
 with torch.no_grad():
     for _ in range(2):
-        net.query(rays, z, aud, expr, lat)
+        run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    net.query(rays, z, aud, expr, lat)
+    run()
     e1.record()
     torch.cuda.synchronize()
 buf = np.zeros((148, 16), np.uint64)
