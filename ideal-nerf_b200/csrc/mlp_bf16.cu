@@ -631,6 +631,9 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                     if constexpr (TRACE) { const long long q1 = clock64(); te_wait += q1 - q0; q0 = q1; }
                     uint32_t packed[64];
                     const int nchunk = NH >> 5;      // 4 (N=256) or 2 (N=128)
+                    // training: this row's mask words of the half (one pointer per half instead of a 64-bit index product per chunk)
+                    uint32_t* mask_half = SAVE ? a.save_mask + (((size_t)chunk * 2 + slot) * TRAIN_MASK_WORDS + train_mask_of(l) + ((h * NH) >> 5)) * 128 + row
+                                               : nullptr;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         if (c < nchunk && !(ABL & 1)) {
@@ -658,7 +661,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                                 default: epi_convert<0, TRACE, SAVE>(r, &packed[c * 16], nullptr, nullptr, nullptr, alpha, rgb0, rgb1, rgb2, tr, dump, neg); break;
                             }
                             if (SAVE && !SAVE_OFF(1) && chunk_ok)      // training: the ReLU mask word of the chunk (the activations follow as a bulk copy of the smem image)
-                                a.save_mask[(((size_t)chunk * 2 + slot) * TRAIN_MASK_WORDS + train_mask_of(l) + (f0 >> 5)) * 128 + row] = ~neg;
+                                mask_half[c * 128] = ~neg;
                             if (!SAVE && h == 1 && l != 10) {
                                 // second half: nothing reads these K-blocks any more (its own MMAs are complete), so each chunk goes to shared
                                 // memory as soon as it is converted and drains behind the next chunk's load instead of in front of the fence
@@ -666,7 +669,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                                 const int ch0 = (f0 & 63) >> 3;
 #pragma unroll
                                 for (int q = 0; q < 4; ++q)
-                                    *reinterpret_cast<uint4*>(kb + (((ch0 + q) ^ rsw) << 4)) =
+                                    *reinterpret_cast<uint4*>(kb + soff[ch0 + q]) =
                                         make_uint4(packed[c * 16 + q * 4], packed[c * 16 + q * 4 + 1], packed[c * 16 + q * 4 + 2], packed[c * 16 + q * 4 + 3]);
                             }
                         }
@@ -696,7 +699,7 @@ __global__ void __launch_bounds__(NTHREADS_BF16, 1) mlp_bf16_kernel(MlpArgs a, i
                                 for (int q = 0; q < 4; ++q) {
                                     uint4 v = make_uint4(packed[c * 16 + q * 4], packed[c * 16 + q * 4 + 1],
                                                          packed[c * 16 + q * 4 + 2], packed[c * 16 + q * 4 + 3]);
-                                    *reinterpret_cast<uint4*>(kb + (((ch0 + q) ^ rsw) << 4)) = v;
+                                    *reinterpret_cast<uint4*>(kb + soff[ch0 + q]) = v;
                                 }
                             }
                         }
