@@ -7,6 +7,9 @@
 //   L0 63->256, L1-4 256->256, L5 (63+256)->256, L6-7 256->256, alpha 256->1,
 //   V0 (256 [+27 view cols])->128, V1-2 128->128, rgb 128->3.
 //
+// Shipped form: clusters of TWO CTAs (template parameter PAIR, tcgen05 cta_group::2): one M = 256 MMA over both CTAs' rows, the weight
+// stages split across the pair -- see the comment above the kernel.  The decomposition below is per CTA and is the same in both forms.
+//
 // Work decomposition (one persistent CTA per SM, 512 threads):
 //   * a CTA iteration owns 256 consecutive points = two 128-row "slots" that advance in lock step,
 //     so every streamed weight byte feeds 256 rows (halves the L2->SM weight traffic of a 128-row tile);
