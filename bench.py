@@ -379,6 +379,35 @@ def sampling_standalone(M, dev, n_rays, reps=20):
     return out
 
 
+def fused_stage_rooflines(net, dev, res, peak_gbs, reps=7):
+    """The three small kernels of the shipped path (inerf_render_rays_fused) on the benchmark frame: device time between CUDA events the
+    measurement twin of the entry records around its five stages (inerf_debug_render_stage_ms), median over `reps` frames.  Algorithmic
+    bytes per ray (SURVEY.md 8d, 64 + 128 samples): set-up 44 (rays) + 256 (z) out; coarse raw2outputs + sampling 1 024 (raw) + 256 (z) +
+    44 + 12 (ray, background) in, 768 (merged z) + 28 (maps, z_std) out; final raw2outputs 3 072 + 768 + 56 in, 28 out."""
+    from ideal_nerf_b200 import ops
+    a = net.args
+    gen = dict(H=H, W=W, focal=net.focal, cx=W * .5, cy=H * .5, near=net.near, far=net.far, c2w=res["pose"][:3, :4], first=0, count=N_RAYS)
+    cond = (res["aud"], res["expr"], res["latent"])
+    ms = []
+    with torch.no_grad():
+        for i in range(reps + 2):
+            out = []
+            ops.render_rays_fused(net.face_nerf_coarse, net.face_nerf_fine, cond, cond, res["bc"], a.N_samples, a.N_importance, 1.0, gen=gen,
+                                  stage_ms=out)
+            if i >= 2:
+                ms.append(out[0])
+    med = [sorted(m[k] for m in ms)[len(ms) // 2] for k in range(5)]
+    nbytes = {"render_setup (2 folds + rays + coarse depths)": (0, 300), "composite_sample_64_128 (coarse raw2outputs + sampler)": (2, 2132),
+              "composite_final (fine raw2outputs, flags, rng)": (4, 3924)}
+    out = {"stage_ms": {"setup": med[0], "mlp_coarse": med[1], "composite_sample": med[2], "mlp_fine": med[3], "composite_final": med[4]},
+           "how": "inerf_debug_render_stage_ms: CUDA events between the five launches of one fused call, median of %d frames" % reps,
+           "kernels": {}}
+    for name, (k, b) in nbytes.items():
+        gbs = N_RAYS * b / (med[k] * 1e-3) / 1e9
+        out["kernels"][name] = {"ms": med[k], "bytes": N_RAYS * b, "achieved": gbs, "frac": gbs / peak_gbs}
+    return out
+
+
 def build_torso_network(mode, dev):
     """BASELINE.json config 4: head + torso renderer (train_torso.py:186), random init + density preset on all four FaceNeRFs."""
     import ideal_nerf_b200 as M
@@ -551,6 +580,7 @@ def run_ours(args):
         with torch.no_grad():
             sa_bytes, sa_ms = composite_standalone(M, dev, N_RAYS)      # always frame-sized: inputs larger than L2
             samp = sampling_standalone(M, dev, N_RAYS)
+            fused_small = fused_stage_rooflines(net, dev, res, pk["hbm_gbs"]) if world == 1 else None
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -582,6 +612,8 @@ def run_ours(args):
                                   "how": "stand-alone on 202 500 rays, 20 back-to-back launches per event pair"},
             "kernels_ms": {k: round(v[1], 3) for k, v in ksum.items()},
         }
+        if fused_small is not None:
+            line["roofline_fused_small"] = fused_small
         if video is not None:
             line["config5_video"] = video
         if train_bf16 is not None:

@@ -84,6 +84,7 @@ SIGNATURES = {
     "inerf_importance_sample": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P]),
     "inerf_render_workspace_bytes": (_I, [ctypes.POINTER(InerfRenderArgs), _SZP]),
     "inerf_render_rays_fused": (_I, [ctypes.POINTER(InerfRenderArgs), _P]),
+    "inerf_debug_render_stage_ms": (_I, [ctypes.POINTER(InerfRenderArgs), _P, ctypes.POINTER(ctypes.c_float)]),
     "inerf_mlp_cond_floats": (_I, [_DIMS, _SZP]),
     "inerf_mlp_fold_cond": (_I, [_DIMS, _PARAMS, _P, _P, _P, _P, _P]),
     "inerf_mlp_packed_bytes": (_I, [_I, _DIMS, _SZP]),

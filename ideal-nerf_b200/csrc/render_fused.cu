@@ -204,7 +204,9 @@ extern "C" int inerf_render_workspace_bytes(const InerfRenderArgs* args, size_t*
     return INERF_OK;
 }
 
-extern "C" int inerf_render_rays_fused(const InerfRenderArgs* a, void* stream) {
+namespace {
+// ev: NULL, or six events recorded on the stream before stage 1 and after each of the five stages (inerf_debug_render_stage_ms)
+int render_rays_fused(const InerfRenderArgs* a, void* stream, cudaEvent_t* ev) {
     Workspace w{};
     int rc = plan(a, w);
     if (rc) return rc;
@@ -229,6 +231,8 @@ extern "C" int inerf_render_rays_fused(const InerfRenderArgs* a, void* stream) {
     if (a->z_vals && ((uintptr_t)a->z_vals & 15)) return fail(INERF_E_ALIGN, "inerf_render_rays_fused: z_vals must be 16-byte aligned");
 
     cudaStream_t st = as_stream(stream);
+    auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], st); };
+    mark(0);
     uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
     auto F = [ws](size_t off) { return reinterpret_cast<float*>(ws + off); };
     const int n = a->n, s1 = a->n_samples, ni = a->n_importance, stot = s1 + ni;
@@ -266,10 +270,12 @@ extern "C" int inerf_render_rays_fused(const InerfRenderArgs* a, void* stream) {
         if (rc) return rc;
     }
 
+    mark(1);
     // ---- 2. coarse FaceNeRF ------------------------------------------------------------------------------------------------------
     rc = inerf_mlp_fwd(a->mode, &a->coarse.dims, a->coarse.params_host, a->coarse.packed, F(w.cond_c), rays, stride, z_c, n, s1, F(w.raw_c), stream);
     if (rc) return rc;
 
+    mark(2);
     // ---- 3. coarse raw2outputs + importance sampling -------------------------------------------------------------------------------
     CompArgs ca{};
     ca.raw = reinterpret_cast<const float4*>(F(w.raw_c)); ca.z = z_c; ca.rays = rays; ca.ray_stride = stride; ca.bc_rgb = a->bc_rgb;
@@ -301,10 +307,12 @@ extern "C" int inerf_render_rays_fused(const InerfRenderArgs* a, void* stream) {
         }
     }
 
+    mark(3);
     // ---- 4. fine FaceNeRF --------------------------------------------------------------------------------------------------------
     rc = inerf_mlp_fwd(a->mode, &a->fine.dims, a->fine.params_host, a->fine.packed, F(w.cond_f), rays, stride, z_m, n, stot, F(w.raw_f), stream);
     if (rc) return rc;
 
+    mark(4);
     // ---- 5. final raw2outputs (+ flags, + RNG bump) ----------------------------------------------------------------------------------
     CompArgs fa{};
     fa.raw = reinterpret_cast<const float4*>(F(w.raw_f)); fa.z = z_m; fa.rays = rays; fa.ray_stride = stride; fa.bc_rgb = a->bc_rgb;
@@ -331,5 +339,24 @@ extern "C" int inerf_render_rays_fused(const InerfRenderArgs* a, void* stream) {
         rc = inerf_flag_nonfinite(xs6, ns6, 6, a->nonfinite, stream);
         if (rc) return rc;
     }
+    mark(5);
     return INERF_OK;
+}
+}  // namespace
+
+extern "C" int inerf_render_rays_fused(const InerfRenderArgs* a, void* stream) { return render_rays_fused(a, stream, nullptr); }
+
+extern "C" int inerf_debug_render_stage_ms(const InerfRenderArgs* a, void* stream, float* ms_host5) {
+    if (!ms_host5) return fail(INERF_E_ARG, "inerf_debug_render_stage_ms: NULL");
+    cudaEvent_t ev[6];
+    for (int i = 0; i < 6; ++i)
+        if (cudaEventCreate(&ev[i]) != cudaSuccess) return fail(INERF_E_ARG, "inerf_debug_render_stage_ms: cudaEventCreate failed");
+    int rc = render_rays_fused(a, stream, ev);
+    if (rc == INERF_OK && a && a->n > 0) {
+        cudaError_t e = cudaEventSynchronize(ev[5]);
+        if (e != cudaSuccess) { set_error("inerf_debug_render_stage_ms: %s", cudaGetErrorString(e)); rc = (int)e; }
+        for (int i = 0; i < 5 && rc == INERF_OK; ++i) cudaEventElapsedTime(&ms_host5[i], ev[i], ev[i + 1]);
+    }
+    for (int i = 0; i < 6; ++i) cudaEventDestroy(ev[i]);
+    return rc;
 }

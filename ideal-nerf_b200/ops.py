@@ -411,7 +411,8 @@ def _render_net(net, aud, expr, latent, keep):
 
 
 def render_rays_fused(net_coarse, net_fine, cond_coarse, cond_fine, bc_rgb, n_samples, n_importance, perturb, rays=None, gen=None,
-                      lindisp=False, white_bkgd=False, with_fg=False, want_weights=False, want_z=False, check_numerics=False, state=None):
+                      lindisp=False, white_bkgd=False, with_fg=False, want_weights=False, want_z=False, check_numerics=False, state=None,
+                      stage_ms=None):
     """Network.render_rays under no_grad as ONE C call (inerf_render_rays_fused): five kernel launches in the reference's
     configuration (set-up, coarse FaceNeRF, compositor + sampler, fine FaceNeRF, final compositor).  rays: packed (n, 11), or
     gen = dict(H, W, focal, cx, cy, near, far, c2w, first, count) to generate the rays of pixels [first, first + count) on the fly.
@@ -470,7 +471,12 @@ def render_rays_fused(net_coarse, net_fine, cond_coarse, cond_fine, bc_rgb, n_sa
     if n > 0:
         with torch.cuda.device(dev):
             fast = a.perturb and n_samples == 64 and n_importance == 128 and not lindisp
-            call("inerf_render_rays_fused", _lib.lib().inerf_render_rays_fused, ctypes.byref(a), stream(), launches=5 if fast else 7)
+            if stage_ms is not None:      # measurement: device time of the five stages (synchronises), appended to the caller's list
+                ms = (ctypes.c_float * 5)()
+                call("inerf_render_rays_fused", _lib.lib().inerf_debug_render_stage_ms, ctypes.byref(a), stream(), ms, launches=5 if fast else 7)
+                stage_ms.append([float(v) for v in ms])
+            else:
+                call("inerf_render_rays_fused", _lib.lib().inerf_render_rays_fused, ctypes.byref(a), stream(), launches=5 if fast else 7)
     ret["_depth_map"] = ret.pop("depth_map")
     if flag is not None:
         bits = int(flag.item())

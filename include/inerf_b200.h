@@ -270,6 +270,10 @@ typedef struct InerfRenderArgs {
  * depths, and the coarse weights / samples of the deterministic path). */
 int inerf_render_workspace_bytes(const InerfRenderArgs* args, size_t* bytes);
 int inerf_render_rays_fused(const InerfRenderArgs* args, void* stream);
+/* Measurement twin (the one entry point that SYNCHRONISES): the same call with a CUDA event between the stages; ms_host5 (HOST, 5 floats)
+ * = device time of {set-up, coarse FaceNeRF, coarse raw2outputs + sampling, fine FaceNeRF, final raw2outputs}.  bench.py uses it for
+ * the rooflines of the fused small kernels. */
+int inerf_debug_render_stage_ms(const InerfRenderArgs* args, void* stream, float* ms_host5);
 
 /* ---- FaceNeRF MLP --------------------------------------------------------------------------- */
 

@@ -1225,6 +1225,13 @@ def test_fused_render_entry_bit_matches_stage_calls(M, golden, mode):
             ops.FUSED_RENDER = True
         for k in ("rgb_map", "disp_map", "acc_map", "rgb0", "z_std", "last_weight"):
             assert bits_equal(a[k], b[k]), ("gen", perturb, k)
+    # the measurement twin (inerf_debug_render_stage_ms): same outputs, five positive stage times
+    ops.seed_rng(99, DEV)
+    stage = []
+    with torch.no_grad():
+        t = ops.render_rays_fused(net.face_nerf_coarse, net.face_nerf_fine, (aud, expr, lat), (aud, expr, lat), bc2, 64, 128, 1.0, gen=gen, stage_ms=stage)
+    assert len(stage) == 1 and len(stage[0]) == 5 and all(v > 0 for v in stage[0]), stage
+    assert bits_equal(t["rgb_map"], a["rgb_map"])
     # a NaN audio code through the fused kernels' own flags (perturb > 0: compositor + sampler and the final compositor OR the bits)
     bad = aud.clone(); bad[3] = float("nan")
     with torch.no_grad():
